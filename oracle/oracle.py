@@ -1,0 +1,111 @@
+"""ctypes wrapper around the CPU oracle (oracle/degk_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "_build" / "libdegk_oracle.so"
+_SRCS = ("degk_oracle.cpp", "oracle_stiff.inc", "oracle_sde.inc", "oracle_tables.inc")
+
+MODELS = {"lorenz": 0, "henon_heiles": 1, "rober": 2, "decay": 3, "linear15": 4, "gbm": 5,
+          "lorenz_additive": 6, "scalar_sde": 7, "osc_t": 8, "gbm_nd": 9}
+ALGS = {"tsit5": 0, "vern7": 1, "vern9": 2, "rosenbrock23": 3, "rodas4": 4, "rodas5p": 5,
+        "em": 6, "siea": 7}
+RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
+            5: "Singular"}
+
+_lib = None
+
+
+def build(force=False):
+    """Compile the oracle if the .so is missing or older than its sources."""
+    stale = force or not _LIB_PATH.exists() or any(
+        (_HERE / f).stat().st_mtime > _LIB_PATH.stat().st_mtime for f in _SRCS)
+    if stale:
+        subprocess.check_call(["make", "-s", "-C", str(_HERE)])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(_LIB_PATH))
+        _lib.degk_oracle_solve.restype = ctypes.c_int
+        _lib.degk_oracle_solve.argtypes = [
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+            ctypes.c_void_p, ctypes.c_int64,
+            ctypes.c_double, ctypes.c_double, ctypes.c_double,
+            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int, ctypes.c_int]
+        _lib.degk_oracle_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def model_info(model):
+    n, np_, m, d = (ctypes.c_int() for _ in range(4))
+    lib().degk_oracle_model_info(MODELS[model], ctypes.byref(n), ctypes.byref(np_),
+                                 ctypes.byref(m), ctypes.byref(d))
+    return n.value, np_.value, m.value, bool(d.value)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3,
+          saveat=None, save_everystep=True, length=None, seed=0, dtype=np.float32,
+          fma_stages=False, nthreads=0):
+    """Solve a batch; returns dict(ts=(N,len), us=(N,len,n), naccept, nreject, retcode).
+
+    u0: (N,n) or (n,) broadcast; p: (N,np) or (np,) broadcast; tspan: (2,) or (N,2).
+    `length` = number of output rows (the host-side `len` of lowerlevel_solve.jl); required
+    unless saveat is given (-> len(saveat)) or endpoints-only (-> 2).
+    """
+    dtype = np.dtype(dtype)
+    n, npar, _, _ = model_info(model)
+    u0 = np.ascontiguousarray(u0, dtype=dtype)
+    p = np.ascontiguousarray(p if p is not None else np.zeros(max(npar, 1)), dtype=dtype)
+    tspan = np.ascontiguousarray(tspan, dtype=dtype)
+    N = max(u0.shape[0] if u0.ndim == 2 else 1, p.shape[0] if p.ndim == 2 else 1,
+            tspan.shape[0] if tspan.ndim == 2 else 1)
+    u0s = n if u0.ndim == 2 else 0
+    ps = p.shape[1] if p.ndim == 2 else 0
+    tss = 2 if tspan.ndim == 2 else 0
+    if saveat is not None:
+        saveat = np.ascontiguousarray(saveat, dtype=dtype)
+        length = len(saveat)
+    elif length is None:
+        if not save_everystep:
+            length = 2
+        else:
+            raise ValueError("length required for save_everystep without saveat")
+    t0 = tspan.reshape(-1, 2)[:, 0]
+    ts = np.empty((N, length), dtype=dtype)
+    ts[:] = t0[:, None] if tspan.ndim == 2 else t0[0]
+    us = np.zeros((N, length, n), dtype=dtype)
+    na = np.zeros(N, np.int32)
+    nr = np.zeros(N, np.int32)
+    rc = np.zeros(N, np.int32)
+    r = lib().degk_oracle_solve(
+        0 if dtype == np.float32 else 1, MODELS[model], ALGS[alg], int(adaptive), N,
+        _ptr(u0), u0s, _ptr(p), ps, _ptr(tspan), tss,
+        float(dtype.type(dt)), float(dtype.type(abstol)), float(dtype.type(reltol)),
+        _ptr(saveat), 0 if saveat is None else len(saveat), int(save_everystep), int(seed),
+        _ptr(us), _ptr(ts), length, _ptr(na), _ptr(nr), _ptr(rc), int(fma_stages), int(nthreads))
+    if r != 0:
+        raise RuntimeError(f"oracle error {r}")
+    return dict(ts=ts, us=us, naccept=na, nreject=nr, retcode=rc)
+
+
+def num_threads():
+    return lib().degk_oracle_num_threads()
