@@ -1,0 +1,33 @@
+"""diffeqgpu.jl_b200 -- B200-native engine behind DiffEqGPU.jl's `EnsembleGPUKernel` path.
+
+Host-side mirror of the reference's operator interface (same names and argument meaning):
+
+    vectorized_solve / vectorized_asolve      src/ensemblegpukernel/lowerlevel_solve.jl
+    GPUTsit5 ... GPUSIEA, EnsembleGPUKernel   gpukernel_algorithms.jl, src/algorithms.jl
+    make_prob_compatible                      src/utils.jl
+    solve(EnsembleProblem, alg, EnsembleGPUKernel; ...)   src/solve.jl (batch glue)
+
+All numerics run in hand-written sm_100a CUDA kernels inside `libdegk.so`, reached through the
+C ABI in include/degk.h.  There is no CPU fallback: importing works anywhere, solving needs a GPU.
+
+The directory name contains a dot, so import it through the `diffeqgpu_b200` shim module at
+the repository root:  `import diffeqgpu_b200 as dg`.
+"""
+from . import _lib, models
+from ._lib import DegkError
+from .algorithms import (EnsembleGPUKernel, GPUEM, GPUODEAlgorithm, GPUODEImplicitAlgorithm,
+                         GPURodas4, GPURodas5P, GPURosenbrock23, GPUSDEAlgorithm, GPUSIEA,
+                         GPUTsit5, GPUVern7, GPUVern9, alg_order)
+from .lowerlevel_solve import Range, get_program, vectorized_asolve, vectorized_solve
+from .problems import (EnsembleContext, EnsembleProblem, ODEFunction, ODEProblem, ProblemBatch,
+                       SDEFunction, SDEProblem, adapt, make_prob_compatible, remake)
+from .solve import EnsembleSolution, ODESolution, solve, solve_host
+
+__all__ = [
+    "DegkError", "EnsembleGPUKernel", "GPUEM", "GPUODEAlgorithm", "GPUODEImplicitAlgorithm",
+    "GPURodas4", "GPURodas5P", "GPURosenbrock23", "GPUSDEAlgorithm", "GPUSIEA", "GPUTsit5",
+    "GPUVern7", "GPUVern9", "alg_order", "Range", "get_program", "vectorized_asolve",
+    "vectorized_solve", "EnsembleContext", "EnsembleProblem", "ODEFunction", "ODEProblem",
+    "ProblemBatch", "SDEFunction", "SDEProblem", "adapt", "make_prob_compatible", "remake",
+    "EnsembleSolution", "ODESolution", "solve", "solve_host", "models",
+]

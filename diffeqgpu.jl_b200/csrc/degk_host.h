@@ -1,0 +1,47 @@
+// degk_host.h -- host-side object layouts shared by degk_api.cu and degk_jit.cpp.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "../../include/degk.h"
+
+#define DEGK_NCOUNTERS 256   // ring of work-queue counters (one per in-flight adaptive launch)
+#define DEGK_NSTREAMS 3      // streams used by degk_solve_host to overlap H2D / solve / D2H
+#define DEGK_NWSBUF 12
+
+namespace degk { struct KArgs; }
+
+struct degk_wsbuf { void* ptr = nullptr; size_t cap = 0; };
+struct degk_workspace { degk_wsbuf bufs[DEGK_NWSBUF]; };
+
+struct degk_ctx {
+    int device = 0, sm_count = 0, cc_major = 0, cc_minor = 0;
+    std::mutex mu;            // guards err
+    std::mutex host_mu;       // serialises degk_solve_host (per-ctx workspaces)
+    std::string err, err_copy;
+    unsigned long long* d_counters = nullptr;
+    std::atomic<unsigned> next_counter{0};
+    cudaStream_t streams[DEGK_NSTREAMS] = {nullptr, nullptr, nullptr};
+    degk_workspace work[DEGK_NSTREAMS];
+    void* d_saveat = nullptr; size_t saveat_cap = 0;
+};
+
+struct degk_program {
+    degk_ctx* ctx = nullptr;
+    degk_program_info info;
+    bool is_sde = false;
+    const void* fn[2] = {nullptr, nullptr};   // AOT kernels: [0] fixed-dt / SDE, [1] adaptive
+    void* jit_module = nullptr;               // CUmodule
+    void* jit_fn[2] = {nullptr, nullptr};     // CUfunction
+};
+
+void degk_set_error(degk_ctx* ctx, const char* fmt, ...);
+
+// NVRTC path (degk_jit.cpp)
+int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog);
+int degk_jit_launch(degk_program* prog, int which, unsigned grid, unsigned block,
+                    const degk::KArgs* args, cudaStream_t stream);
+void degk_jit_release(degk_program* prog);

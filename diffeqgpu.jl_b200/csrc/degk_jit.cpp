@@ -1,0 +1,338 @@
+// degk_jit.cpp -- run-time specialisation of the stepper kernels on a user model via NVRTC.
+//
+// Replaces what GPUCompiler does for the reference at the first call of a kernel
+// (src/ensemblegpukernel/lowerlevel_solve.jl:113, :182-188, :333): the user's RHS / Jacobian /
+// tgrad / noise function bodies are spliced into a model struct, the same device headers that
+// libdegk's ahead-of-time kernels are built from are handed to NVRTC as in-memory includes, and
+// the result is compiled straight to sm_100a SASS so state, parameters and stage vectors stay in
+// registers and the tableau coefficients become immediates.
+//
+// libnvrtc and the driver API are resolved lazily (dlopen / cudaGetDriverEntryPoint) so that
+// libdegk.so itself loads on machines without a GPU driver.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "degk_host.h"
+#include "degk_internal.h"
+#include "degk_embedded.inc"   // generated: degk_embedded_names[], degk_embedded_sources[], degk_embedded_count
+
+namespace {
+
+// ---- NVRTC, loaded on demand ----
+typedef void* nvrtcProgram;
+struct Nvrtc {
+    void* h = nullptr;
+    int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+    int (*CompileProgram)(nvrtcProgram, int, const char* const*);
+    int (*GetProgramLogSize)(nvrtcProgram, size_t*);
+    int (*GetProgramLog)(nvrtcProgram, char*);
+    int (*GetCUBINSize)(nvrtcProgram, size_t*);
+    int (*GetCUBIN)(nvrtcProgram, char*);
+    int (*DestroyProgram)(nvrtcProgram*);
+    const char* (*GetErrorString)(int);
+    int (*Version)(int*, int*);
+    std::string load_error;
+};
+Nvrtc g_nvrtc;
+std::once_flag g_nvrtc_once;
+
+void load_nvrtc() {
+    const char* cands[] = {getenv("DEGK_NVRTC_LIB"), "libnvrtc.so.12", "libnvrtc.so",
+                           "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* c : cands) {
+        if (!c || !*c) continue;
+        g_nvrtc.h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+        if (g_nvrtc.h) break;
+        g_nvrtc.load_error += std::string(c) + ": " + dlerror() + "; ";
+    }
+    if (!g_nvrtc.h) return;
+#define SYM(field, name)                                                        \
+    *(void**)(&g_nvrtc.field) = dlsym(g_nvrtc.h, name);                         \
+    if (!g_nvrtc.field) { g_nvrtc.load_error = std::string("missing symbol ") + name; dlclose(g_nvrtc.h); g_nvrtc.h = nullptr; return; }
+    SYM(CreateProgram, "nvrtcCreateProgram")
+    SYM(CompileProgram, "nvrtcCompileProgram")
+    SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    SYM(GetProgramLog, "nvrtcGetProgramLog")
+    SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    SYM(GetCUBIN, "nvrtcGetCUBIN")
+    SYM(DestroyProgram, "nvrtcDestroyProgram")
+    SYM(GetErrorString, "nvrtcGetErrorString")
+    SYM(Version, "nvrtcVersion")
+#undef SYM
+}
+
+// ---- driver API through the runtime (no link-time dependency on libcuda) ----
+struct Driver {
+    bool ok = false;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*);
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+    CUresult (*ModuleUnload)(CUmodule);
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, CUstream, void**, void**);
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction);
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
+    CUresult (*GetErrorString)(CUresult, const char**);
+    std::string load_error;
+};
+Driver g_drv;
+std::once_flag g_drv_once;
+
+void load_driver() {
+    cudaFree(nullptr);   // make sure the primary context exists
+#define DSYM(field, name)                                                                         \
+    {                                                                                             \
+        void* fp = nullptr;                                                                       \
+        cudaDriverEntryPointQueryResult qr;                                                       \
+        cudaError_t e = cudaGetDriverEntryPoint(name, &fp, cudaEnableDefault, &qr);               \
+        if (e != cudaSuccess || !fp) { g_drv.load_error = std::string("driver symbol ") + name + " unavailable"; return; } \
+        *(void**)(&g_drv.field) = fp;                                                             \
+    }
+    DSYM(ModuleLoadData, "cuModuleLoadData")
+    DSYM(ModuleGetFunction, "cuModuleGetFunction")
+    DSYM(ModuleUnload, "cuModuleUnload")
+    DSYM(LaunchKernel, "cuLaunchKernel")
+    DSYM(FuncGetAttribute, "cuFuncGetAttribute")
+    DSYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+    DSYM(GetErrorString, "cuGetErrorString")
+#undef DSYM
+    g_drv.ok = true;
+}
+
+const char* method_header(int alg) {
+    switch (alg) {
+    case DEGK_ALG_TSIT5: return "gen_erk_tsit5.cuh";
+    case DEGK_ALG_VERN7: return "gen_erk_vern7.cuh";
+    case DEGK_ALG_VERN9: return "gen_erk_vern9.cuh";
+    case DEGK_ALG_ROSENBROCK23: case DEGK_ALG_RODAS4: case DEGK_ALG_RODAS5P: return "degk_rosenbrock.cuh";
+    default: return "degk_sde_kernels.cuh";
+    }
+}
+const char* method_type(int alg) {
+    switch (alg) {
+    case DEGK_ALG_TSIT5: return "degk::ErkTsit5<REAL, MODEL>";
+    case DEGK_ALG_VERN7: return "degk::ErkVern7<REAL, MODEL>";
+    case DEGK_ALG_VERN9: return "degk::ErkVern9<REAL, MODEL>";
+    case DEGK_ALG_ROSENBROCK23: return "degk::Rosenbrock23<REAL, MODEL>";
+    case DEGK_ALG_RODAS4: return "degk::Rodas<REAL, MODEL, false>";
+    case DEGK_ALG_RODAS5P: return "degk::Rodas<REAL, MODEL, true>";
+    default: return "";
+    }
+}
+const char* builtin_struct(const char* name) {
+    static const char* map[][2] = {{"lorenz", "Lorenz"}, {"henon_heiles", "HenonHeiles"}, {"rober", "Rober"},
+                                   {"decay", "Decay"}, {"linear15", "Linear15"}, {"gbm", "Gbm"},
+                                   {"scalar_sde", "ScalarSde"}, {"osc_t", "OscT"}, {"gbm_nd", "GbmNd"}};
+    for (auto& m : map) if (strcmp(m[0], name) == 0) return m[1];
+    return nullptr;
+}
+
+}  // namespace
+
+// Build the translation unit handed to NVRTC.
+static int make_source(degk_ctx* ctx, const degk_model_desc* d, std::string& src) {
+    const bool is_sde = d->alg == DEGK_ALG_EM || d->alg == DEGK_ALG_SIEA;
+    const bool stiff = d->alg >= DEGK_ALG_ROSENBROCK23 && d->alg <= DEGK_ALG_RODAS5P;
+    char buf[512];
+    src += "#include \"degk_common.cuh\"\n";
+    src += std::string("#include \"") + method_header(d->alg) + "\"\n";
+    src += is_sde ? "#include \"degk_sde_kernels.cuh\"\n" : "#include \"degk_ode_kernels.cuh\"\n";
+    snprintf(buf, sizeof buf, "typedef %s REAL;\n", d->dtype == DEGK_F64 ? "double" : "float");
+    src += buf;
+    if (d->rhs_src) {
+        if (d->n_state <= 0 || d->n_state > 64 || d->n_param < 0 || d->n_noise < 0) {
+            degk_set_error(ctx, "n_state must be in 1..64 and n_param, n_noise >= 0");
+            return DEGK_ERR_INVALID;
+        }
+        if (stiff && !d->jac_src) {
+            // reference: nlsolve/type.jl:131-137 falls back to ForwardDiff / finite differences;
+            // that lowering is not available here
+            degk_set_error(ctx, "the stiff solvers need an analytic Jacobian body (jac_src)");
+            return DEGK_ERR_UNSUPPORTED;
+        }
+        if (is_sde && !d->noise_src) { degk_set_error(ctx, "SDE solvers need noise_src"); return DEGK_ERR_INVALID; }
+        const int noise = is_sde ? d->noise_kind : 0;
+        const int m = noise == DEGK_NOISE_GENERAL ? d->n_noise : d->n_state;
+        src += "namespace degk {\nstruct UserModel {\n";
+        snprintf(buf, sizeof buf,
+                 "    static constexpr int N = %d, NP = %d, M = %d, NOISE = %d;\n"
+                 "    static constexpr bool HAS_JAC = %s, HAS_TGRAD = %s;\n",
+                 d->n_state, d->n_param, m, noise, d->jac_src ? "true" : "false", d->jac_src ? "true" : "false");
+        src += buf;
+        src += "    template <class T> static DEGK_DEV void f(T (&du)[N], const T (&u)[N], const T* p, T t) {\n";
+        src += d->rhs_src;
+        src += "\n    }\n";
+        if (d->jac_src) {
+            src += "    template <class T> static DEGK_DEV void jac(T (&J)[N][N], const T (&u)[N], const T* p, T t) {\n"
+                   "        DEGK_UNROLL for (int i_ = 0; i_ < N; ++i_) DEGK_UNROLL for (int j_ = 0; j_ < N; ++j_) J[i_][j_] = (T)0;\n";
+            src += d->jac_src;
+            src += "\n    }\n";
+            src += "    template <class T> static DEGK_DEV void tgrad(T (&dT)[N], const T (&u)[N], const T* p, T t) {\n"
+                   "        DEGK_UNROLL for (int i_ = 0; i_ < N; ++i_) dT[i_] = (T)0;\n";
+            if (d->tgrad_src) src += d->tgrad_src;
+            src += "\n    }\n";
+        }
+        if (noise == DEGK_NOISE_DIAGONAL) {
+            src += "    template <class T> static DEGK_DEV void g(T (&g)[N], const T (&u)[N], const T* p, T t) {\n";
+            src += d->noise_src;
+            src += "\n    }\n";
+        } else if (noise == DEGK_NOISE_GENERAL) {
+            src += "    template <class T> static DEGK_DEV void G(T (&G)[N][M], const T (&u)[N], const T* p, T t) {\n"
+                   "        DEGK_UNROLL for (int i_ = 0; i_ < N; ++i_) DEGK_UNROLL for (int j_ = 0; j_ < M; ++j_) G[i_][j_] = (T)0;\n";
+            src += d->noise_src;
+            src += "\n    }\n";
+        }
+        src += "};\n}\ntypedef degk::UserModel MODEL;\n";
+    } else {
+        const char* st = d->builtin ? builtin_struct(d->builtin) : nullptr;
+        if (!st) { degk_set_error(ctx, "unknown built-in model '%s'", d->builtin ? d->builtin : "(null)"); return DEGK_ERR_INVALID; }
+        src += "#include \"degk_models.cuh\"\n";
+        src += std::string("typedef degk::") + st + " MODEL;\n";
+    }
+    snprintf(buf, sizeof buf, "#define DEGK_JIT_BLOCK %d\n", DEGK_BLOCK);
+    src += buf;
+    if (is_sde) {
+        snprintf(buf, sizeof buf,
+                 "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
+                 "    degk::sde_solve_body<REAL, MODEL, %s>(a);\n}\n",
+                 d->alg == DEGK_ALG_EM ? "degk::ALG_EM" : "degk::ALG_SIEA");
+        src += buf;
+    } else {
+        src += std::string("typedef ") + method_type(d->alg) + " METHOD;\n";
+        src += "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
+               "    degk::ode_solve_body<REAL, MODEL, METHOD>(a);\n}\n"
+               "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_adaptive(const degk::KArgs a) {\n"
+               "    degk::ode_asolve_body<REAL, MODEL, METHOD>(a);\n}\n";
+    }
+    src += "extern \"C\" __device__ const int degk_jit_dims[4] = {MODEL::N, MODEL::NP, MODEL::M, MODEL::NOISE};\n";
+    return DEGK_OK;
+}
+
+// Compile to a cubin.  Usable without a GPU (NVRTC is a pure compiler).
+static int compile_cubin(degk_ctx* ctx, const degk_model_desc* d, std::vector<char>& cubin,
+                         std::string& log) {
+    std::call_once(g_nvrtc_once, load_nvrtc);
+    if (!g_nvrtc.h) {
+        degk_set_error(ctx, "cannot load libnvrtc (%s) -- set DEGK_NVRTC_LIB", g_nvrtc.load_error.c_str());
+        return DEGK_ERR_NVRTC;
+    }
+    std::string src;
+    int rc = make_source(ctx, d, src);
+    if (rc != DEGK_OK) return rc;
+    nvrtcProgram prog = nullptr;
+    int e = g_nvrtc.CreateProgram(&prog, src.c_str(), "degk_jit.cu", degk_embedded_count,
+                                  degk_embedded_sources, degk_embedded_names);
+    if (e != 0) { degk_set_error(ctx, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(e)); return DEGK_ERR_NVRTC; }
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+                                     d->fp_mode == DEGK_FP_STRICT ? "-DDEGK_STRICT=1" : "-DDEGK_STRICT=0",
+                                     d->fp_mode == DEGK_FP_STRICT ? "--fmad=false" : "--fmad=true"};
+    e = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
+    size_t ls = 0;
+    g_nvrtc.GetProgramLogSize(prog, &ls);
+    if (ls > 1) { log.resize(ls); g_nvrtc.GetProgramLog(prog, &log[0]); }
+    if (e != 0) {
+        degk_set_error(ctx, "NVRTC compilation failed (%s):\n%.3500s", g_nvrtc.GetErrorString(e), log.c_str());
+        g_nvrtc.DestroyProgram(&prog);
+        return DEGK_ERR_NVRTC;
+    }
+    size_t cs = 0;
+    g_nvrtc.GetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    g_nvrtc.GetCUBIN(prog, cubin.data());
+    g_nvrtc.DestroyProgram(&prog);
+    return DEGK_OK;
+}
+
+extern "C" int degk_jit_compile_check(const degk_model_desc* d, int64_t* cubin_bytes, char* msg, int64_t msg_cap) {
+    std::vector<char> cubin;
+    std::string log;
+    degk_ctx tmp;
+    int rc = compile_cubin(&tmp, d, cubin, log);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    if (msg && msg_cap > 0) {
+        const std::string& m = rc == DEGK_OK ? log : tmp.err;
+        snprintf(msg, (size_t)msg_cap, "%s", m.c_str());
+    }
+    return rc;
+}
+
+#define DRV(ctx, call)                                                                        \
+    do {                                                                                      \
+        CUresult r_ = (call);                                                                 \
+        if (r_ != CUDA_SUCCESS) {                                                             \
+            const char* s_ = nullptr;                                                         \
+            g_drv.GetErrorString(r_, &s_);                                                    \
+            degk_set_error(ctx, "%s failed: %s", #call, s_ ? s_ : "?");                       \
+            return DEGK_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) {
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    std::string log;
+    int rc = compile_cubin(ctx, d, cubin, log);
+    if (rc != DEGK_OK) return rc;
+    std::call_once(g_drv_once, load_driver);
+    if (!g_drv.ok) { degk_set_error(ctx, "CUDA driver API unavailable: %s", g_drv.load_error.c_str()); return DEGK_ERR_CUDA; }
+    CUmodule mod = nullptr;
+    DRV(ctx, g_drv.ModuleLoadData(&mod, cubin.data()));
+    prog->jit_module = mod;
+    const bool is_sde = prog->is_sde;
+    CUfunction f0 = nullptr, f1 = nullptr;
+    DRV(ctx, g_drv.ModuleGetFunction(&f0, mod, "degk_jit_fixed"));
+    if (!is_sde) DRV(ctx, g_drv.ModuleGetFunction(&f1, mod, "degk_jit_adaptive"));
+    prog->jit_fn[0] = f0;
+    prog->jit_fn[1] = f1;
+    prog->info.is_jit = 1;
+    if (d->rhs_src) {
+        const int noise = is_sde ? d->noise_kind : 0;
+        prog->info.n_state = d->n_state; prog->info.n_param = d->n_param;
+        prog->info.n_noise = noise == DEGK_NOISE_GENERAL ? d->n_noise : d->n_state;
+        prog->info.noise_kind = noise;
+    } else {
+        // dims of a JIT-compiled built-in: mirror of degk_models.cuh
+        static const struct { const char* n; int N, NP, M, K; } dims[] = {
+            {"lorenz", 3, 3, 3, 1}, {"henon_heiles", 4, 0, 0, 0}, {"rober", 3, 3, 0, 0}, {"decay", 1, 1, 0, 0},
+            {"linear15", 15, 0, 0, 0}, {"gbm", 3, 2, 3, 1}, {"scalar_sde", 1, 2, 1, 1}, {"osc_t", 2, 1, 0, 0},
+            {"gbm_nd", 2, 2, 4, 2}};
+        for (auto& m : dims)
+            if (strcmp(m.n, d->builtin) == 0) {
+                prog->info.n_state = m.N; prog->info.n_param = m.NP; prog->info.n_noise = m.M; prog->info.noise_kind = m.K;
+            }
+    }
+    int v = 0;
+    DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, f0)); prog->info.regs_fixed = v;
+    DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f0)); prog->info.local_bytes_fixed = v;
+    if (f1) {
+        DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, f1)); prog->info.regs_adaptive = v;
+        DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f1)); prog->info.local_bytes_adaptive = v;
+    }
+    DRV(ctx, g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, f1 ? f1 : f0, DEGK_BLOCK, 0));
+    prog->info.max_blocks_per_sm = v;
+    prog->info.jit_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return DEGK_OK;
+}
+
+int degk_jit_launch(degk_program* prog, int which, unsigned grid, unsigned block,
+                    const degk::KArgs* args, cudaStream_t stream) {
+    degk_ctx* ctx = prog->ctx;
+    CUfunction f = (CUfunction)prog->jit_fn[which];
+    if (!f) { degk_set_error(ctx, "program has no %s kernel", which ? "adaptive" : "fixed-dt"); return DEGK_ERR_UNSUPPORTED; }
+    void* params[1] = {(void*)args};
+    DRV(ctx, g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, (CUstream)stream, params, nullptr));
+    return DEGK_OK;
+}
+
+void degk_jit_release(degk_program* prog) {
+    if (prog->jit_module && g_drv.ok) g_drv.ModuleUnload((CUmodule)prog->jit_module);
+    prog->jit_module = nullptr;
+}

@@ -1,0 +1,346 @@
+// degk_rosenbrock.cuh -- stiff steppers with a register-resident factorisation of W.
+//
+//   Rosenbrock23  reference perform_step/gpu_rosenbrock23_perform_step.jl:1-70, 74-201
+//   Rodas4        reference perform_step/gpu_rodas4_perform_step.jl:1-116, 118-277
+//   Rodas5P       reference perform_step/gpu_rodas5P_perform_step.jl:1-153, 155-351
+//   LinSolve      reference linalg/linsolve.jl:8-57 (n<=3 adjugate), :88-108 + linalg/lu.jl:114-159
+//
+// The reference calls linear_solve(W, b) 2-8 times per attempt with the same W and relies on
+// LLVM to CSE the cofactors / refactorise.  Here W is factored ONCE per attempt into registers
+// (cofactors + det for n<=3, partial-pivot LU for n>=4) and each stage only does the
+// substitution.  The values are identical to recomputing (same expressions), so the strict
+// build stays bit-equal to the oracle.
+// Mass matrix = identity (UniformScaling); mass-matrix/DAE problems are SURVEY §8(f) "next".
+#pragma once
+#include "degk_common.cuh"
+#include "gen_rodas_consts.cuh"
+
+namespace degk {
+
+// ---------------------------------------------------------------------------------------
+template <class T, int N>
+struct LinSolve {
+    T lu[N][N];          // n>=4: L (unit, below diag) and U;  n<=3: cofactor matrix
+    T dinv[N];           // n>=4: 1/U_jj ; n<=3: dinv[0] = det (strict) or 1/det (fast)
+    int piv[N];          // n>=4: row interchanged with row k at elimination step k
+
+    DEGK_DEV bool factor(const T (&A)[N][N]) {
+        if (N == 1) {
+            dinv[0] = (T)1 / A[0][0];
+            return true;
+        } else if (N == 2) {
+            const T d = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+#if DEGK_STRICT
+            dinv[0] = d;
+#else
+            dinv[0] = (T)1 / d;
+#endif
+            lu[0][0] = A[1][1]; lu[0][1] = A[0][1]; lu[1][0] = A[1][0]; lu[1][1] = A[0][0];
+            return true;
+        } else if (N == 3) {
+            const T a11 = A[0][0], a12 = A[0][1], a13 = A[0][2];
+            const T a21 = A[1][0], a22 = A[1][1], a23 = A[1][2];
+            const T a31 = A[2][0], a32 = A[2][1], a33 = A[2][2];
+            lu[0][0] = a22 * a33 - a23 * a32; lu[0][1] = a13 * a32 - a12 * a33; lu[0][2] = a12 * a23 - a13 * a22;
+            lu[1][0] = a23 * a31 - a21 * a33; lu[1][1] = a11 * a33 - a13 * a31; lu[1][2] = a13 * a21 - a11 * a23;
+            lu[2][0] = a21 * a32 - a22 * a31; lu[2][1] = a12 * a31 - a11 * a32; lu[2][2] = a11 * a22 - a12 * a21;
+            // det = x0 . (x1 x x2) over columns (StaticArrays): cross terms equal the first
+            // cofactor column above (products commute), so reuse them.
+            const T d = (a11 * lu[0][0] + a21 * lu[0][1]) + a31 * lu[0][2];
+#if DEGK_STRICT
+            dinv[0] = d;
+#else
+            dinv[0] = (T)1 / d;
+#endif
+            return true;
+        } else {
+            DEGK_UNROLL for (int i = 0; i < N; ++i)
+                DEGK_UNROLL for (int j = 0; j < N; ++j) lu[i][j] = A[i][j];
+            bool ok = true;
+            DEGK_UNROLL for (int k = 0; k < N; ++k) {
+                int kp = k;
+                T amax = abs_(lu[k][k]);
+                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+                    const T v = abs_(lu[i][k]);
+                    if (v > amax) { kp = i; amax = v; }
+                }
+                piv[k] = kp;
+                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+                    if (kp == i) {
+                        DEGK_UNROLL for (int j = 0; j < N; ++j) { const T s = lu[k][j]; lu[k][j] = lu[i][j]; lu[i][j] = s; }
+                    }
+                }
+                const T inv = (T)1 / lu[k][k];
+                const bool fin = finite_(inv);
+                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+                    const T l = fin ? lu[i][k] * inv : (T)0;
+                    lu[i][k] = l;
+                    DEGK_UNROLL for (int j = k + 1; j < N; ++j) lu[i][j] = lu[i][j] - l * lu[k][j];
+                }
+            }
+            DEGK_UNROLL for (int j = 0; j < N; ++j) {
+                if (lu[j][j] == (T)0) ok = false;
+                dinv[j] = (T)1 / lu[j][j];
+            }
+            return ok;
+        }
+    }
+
+    DEGK_DEV void solve(const T (&b)[N], T (&x)[N]) const {
+        if (N == 1) {
+            x[0] = dinv[0] * b[0];
+        } else if (N == 2) {
+#if DEGK_STRICT
+            x[0] = (lu[0][0] * b[0] - lu[0][1] * b[1]) / dinv[0];
+            x[1] = (lu[1][1] * b[1] - lu[1][0] * b[0]) / dinv[0];
+#else
+            x[0] = (lu[0][0] * b[0] - lu[0][1] * b[1]) * dinv[0];
+            x[1] = (lu[1][1] * b[1] - lu[1][0] * b[0]) * dinv[0];
+#endif
+        } else if (N == 3) {
+            DEGK_UNROLL for (int i = 0; i < 3; ++i) {
+                const T s = (lu[i][0] * b[0] + lu[i][1] * b[1]) + lu[i][2] * b[2];
+#if DEGK_STRICT
+                x[i] = s / dinv[0];
+#else
+                x[i] = s * dinv[0];
+#endif
+            }
+        } else {
+            T y[N];
+            DEGK_UNROLL for (int i = 0; i < N; ++i) y[i] = b[i];
+            DEGK_UNROLL for (int k = 0; k < N; ++k) {
+                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+                    if (piv[k] == i) { const T s = y[k]; y[k] = y[i]; y[i] = s; }
+                }
+            }
+            DEGK_UNROLL for (int j = 0; j < N; ++j)
+                DEGK_UNROLL for (int i = j + 1; i < N; ++i) y[i] = y[i] - lu[i][j] * y[j];
+            DEGK_UNROLL for (int j = N - 1; j >= 0; --j) {
+                y[j] = dinv[j] * y[j];
+                DEGK_UNROLL for (int i = j - 1; i >= 0; --i) y[i] = y[i] - lu[i][j] * y[j];
+            }
+            DEGK_UNROLL for (int i = 0; i < N; ++i) x[i] = y[i];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+template <class T, class Model>
+struct Rosenbrock23 {
+    static constexpr int N = Model::N;
+    static constexpr int ORDER = 2;
+    static constexpr bool FSAL = false;
+    struct Keep { T k1[N], k2[N]; };
+    static DEGK_DEV T dtmin() { return (T)1.0e-14f; }     // convert(T, 1.0f-14), SURVEY Q13
+    static DEGK_DEV T land()  { return (T)1.0e-14f; }
+    static DEGK_DEV void init(Keep&, const T (&)[N], const T*, T) {}
+    static DEGK_DEV void accepted(Keep&) {}
+    static DEGK_DEV void on_accept(Keep&) {}
+
+    template <bool WANT_ERR>
+    static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
+                                 T (&unew)[N], T (&err)[N]) {
+        static_assert(Model::HAS_JAC && Model::HAS_TGRAD, "stiff solvers need analytic jac/tgrad");
+        const T two = (T)2;
+        const T d = (T)1 / (two + sqrt_(two));            // stiff/types.jl:47-48
+        const T gam = h * d;
+        const T dto2 = h / (T)2, dto6 = h / (T)6;
+        T J[N][N], W[N][N], dT[N];
+        Model::template jac<T>(J, uprev, p, t);
+        Model::template tgrad<T>(dT, uprev, p, t);
+        DEGK_UNROLL for (int i = 0; i < N; ++i)
+            DEGK_UNROLL for (int j = 0; j < N; ++j) {
+                const T v = -(gam * J[i][j]);
+                W[i][j] = (i == j) ? v + (T)1 : v;
+            }
+        LinSolve<T, N> F;
+        if (!F.factor(W)) return false;
+        T F0[N], F1[N], rhs[N], tmp[N];
+        Model::template f<T>(F0, uprev, p, t);
+        DEGK_UNROLL for (int c = 0; c < N; ++c) rhs[c] = F0[c] + gam * dT[c];
+        F.solve(rhs, K.k1);
+        DEGK_UNROLL for (int c = 0; c < N; ++c) tmp[c] = uprev[c] + dto2 * K.k1[c];
+        Model::template f<T>(F1, tmp, p, t + dto2);
+        DEGK_UNROLL for (int c = 0; c < N; ++c) rhs[c] = F1[c] - K.k1[c];
+        F.solve(rhs, K.k2);
+        DEGK_UNROLL for (int c = 0; c < N; ++c) K.k2[c] = K.k2[c] + K.k1[c];
+        DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uprev[c] + h * K.k2[c];
+        if (WANT_ERR) {
+            const T e32 = (T)6 + sqrt_((T)2);
+            T F2[N], k3[N];
+            Model::template f<T>(F2, unew, p, t + h);
+            DEGK_UNROLL for (int c = 0; c < N; ++c)
+                rhs[c] = ((F2[c] - e32 * (K.k2[c] - F1[c])) - two * (K.k1[c] - F0[c])) + h * dT[c];
+            F.solve(rhs, k3);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) err[c] = dto6 * ((K.k1[c] - two * K.k2[c]) + k3[c]);
+        }
+        return true;
+    }
+
+    // nonstiff/interpolants.jl:389-399
+    static DEGK_DEV void interp(const Keep& K, T theta, T h, const T (&uprev)[N],
+                                const T (&unew)[N], const T* p, T tprev, T (&out)[N]) {
+        const T two = (T)2;
+        const T d = (T)1 / (two + sqrt_(two));
+        const T den = fma_((T)-2, d, (T)1);
+        const T c1 = theta * ((T)1 - theta) / den;
+        const T c2 = theta * fma_((T)-2, d, theta) / den;
+        DEGK_UNROLL for (int c = 0; c < N; ++c)
+            out[c] = fma_(h, fma_(c2, K.k2[c], c1 * K.k1[c]), uprev[c]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Rodas4 (6 stages) and Rodas5P (8 stages) share the structure; R5 selects the tableau.
+template <class T, class Model, bool R5>
+struct Rodas {
+    static constexpr int N = Model::N;
+    static constexpr int ORDER = R5 ? 5 : 4;
+    static constexpr bool FSAL = false;
+    static constexpr int NS = R5 ? 8 : 6;
+    struct Keep { T ks[NS][N]; T kk[3][N]; };
+    static DEGK_DEV T dtmin() { return (T)1.0e-14f; }
+    static DEGK_DEV T land()  { return (T)1.0e-14f; }
+    static DEGK_DEV void init(Keep&, const T (&)[N], const T*, T) {}
+    static DEGK_DEV void accepted(Keep&) {}
+
+#define R4C(x) ((T)rodas4c::x)
+#define R5C(x) ((T)rodas5pc::x)
+#define RC(x) (R5 ? R5C(x) : R4C(x))
+
+    template <bool WANT_ERR>
+    static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
+                                 T (&unew)[N], T (&err)[N]) {
+        static_assert(Model::HAS_JAC && Model::HAS_TGRAD, "stiff solvers need analytic jac/tgrad");
+        T J[N][N], dT[N];
+        Model::template jac<T>(J, uprev, p, t);
+        Model::template tgrad<T>(dT, uprev, p, t);
+        const T dtgamma = h * RC(gamma);
+        const T invdg = (T)1 / dtgamma;
+        DEGK_UNROLL for (int i = 0; i < N; ++i) J[i][i] = J[i][i] - invdg;    // W = J - I/(dt*gamma)
+        LinSolve<T, N> F;
+        if (!F.factor(J)) return false;
+        T (&k)[NS][N] = K.ks;
+        T du[N], lt[N], uu[N];
+        Model::template f<T>(du, uprev, p, t);
+        // Step 1
+        { const T dtd1 = h * RC(d1);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + dtd1 * dT[c]); }
+        F.solve(lt, k[0]);
+        DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uprev[c] + RC(a21) * k[0][c];
+        Model::template f<T>(du, uu, p, t + RC(c2) * h);
+        // Step 2
+        { const T dtd2 = h * RC(d2), C21 = RC(C21) / h;
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd2 * dT[c]) + C21 * k[0][c]); }
+        F.solve(lt, k[1]);
+        DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = (uprev[c] + RC(a31) * k[0][c]) + RC(a32) * k[1][c];
+        Model::template f<T>(du, uu, p, t + RC(c3) * h);
+        // Step 3
+        { const T dtd3 = h * RC(d3), C31 = RC(C31) / h, C32 = RC(C32) / h;
+          DEGK_UNROLL for (int c = 0; c < N; ++c)
+              lt[c] = -((du[c] + dtd3 * dT[c]) + (C31 * k[0][c] + C32 * k[1][c])); }
+        F.solve(lt, k[2]);
+        DEGK_UNROLL for (int c = 0; c < N; ++c)
+            uu[c] = ((uprev[c] + RC(a41) * k[0][c]) + RC(a42) * k[1][c]) + RC(a43) * k[2][c];
+        Model::template f<T>(du, uu, p, t + RC(c4) * h);
+        // Step 4
+        { const T dtd4 = h * RC(d4), C41 = RC(C41) / h, C42 = RC(C42) / h, C43 = RC(C43) / h;
+          DEGK_UNROLL for (int c = 0; c < N; ++c)
+              lt[c] = -((du[c] + dtd4 * dT[c]) + ((C41 * k[0][c] + C42 * k[1][c]) + C43 * k[2][c])); }
+        F.solve(lt, k[3]);
+        DEGK_UNROLL for (int c = 0; c < N; ++c)
+            uu[c] = (((uprev[c] + RC(a51) * k[0][c]) + RC(a52) * k[1][c]) + RC(a53) * k[2][c]) + RC(a54) * k[3][c];
+        const T C51 = RC(C51) / h, C52 = RC(C52) / h, C53 = RC(C53) / h, C54 = RC(C54) / h;
+        if (R5) {
+            Model::template f<T>(du, uu, p, t + R5C(c5) * h);
+            // Step 5: summands in the order k2,k4,k1,k3 (gpu_rodas5P_perform_step.jl:271)
+            { const T dtd5 = h * R5C(d5);
+              DEGK_UNROLL for (int c = 0; c < N; ++c)
+                  lt[c] = -((du[c] + dtd5 * dT[c]) +
+                            (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c])); }
+            F.solve(lt, k[4]);
+            DEGK_UNROLL for (int c = 0; c < N; ++c)
+                uu[c] = ((((uprev[c] + R5C(a61) * k[0][c]) + R5C(a62) * k[1][c]) + R5C(a63) * k[2][c]) +
+                         R5C(a64) * k[3][c]) + R5C(a65) * k[4][c];
+            Model::template f<T>(du, uu, p, t + h);
+            // Step 6
+            { const T C61 = R5C(C61) / h, C62 = R5C(C62) / h, C63 = R5C(C63) / h, C64 = R5C(C64) / h, C65 = R5C(C65) / h;
+              DEGK_UNROLL for (int c = 0; c < N; ++c)
+                  lt[c] = -(du[c] + ((((C61 * k[0][c] + C62 * k[1][c]) + C63 * k[2][c]) + C64 * k[3][c]) + C65 * k[4][c])); }
+            F.solve(lt, k[5]);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[5][c];
+            Model::template f<T>(du, uu, p, t + h);
+            // Step 7
+            { const T C71 = R5C(C71) / h, C72 = R5C(C72) / h, C73 = R5C(C73) / h, C74 = R5C(C74) / h,
+                      C75 = R5C(C75) / h, C76 = R5C(C76) / h;
+              DEGK_UNROLL for (int c = 0; c < N; ++c)
+                  lt[c] = -(du[c] + (((((C71 * k[0][c] + C72 * k[1][c]) + C73 * k[2][c]) + C74 * k[3][c]) +
+                                      C75 * k[4][c]) + C76 * k[5][c])); }
+            F.solve(lt, k[NS > 6 ? 6 : 0]);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[NS > 6 ? 6 : 0][c];
+            Model::template f<T>(du, uu, p, t + h);
+            // Step 8
+            { const T C81 = R5C(C81) / h, C82 = R5C(C82) / h, C83 = R5C(C83) / h, C84 = R5C(C84) / h,
+                      C85 = R5C(C85) / h, C86 = R5C(C86) / h, C87 = R5C(C87) / h;
+              DEGK_UNROLL for (int c = 0; c < N; ++c)
+                  lt[c] = -(du[c] + ((((((C81 * k[0][c] + C82 * k[1][c]) + C83 * k[2][c]) + C84 * k[3][c]) +
+                                       C85 * k[4][c]) + C86 * k[5][c]) + C87 * k[NS > 6 ? 6 : 0][c])); }
+            F.solve(lt, k[NS - 1]);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uu[c] + k[NS - 1][c];
+        } else {
+            Model::template f<T>(du, uu, p, t + h);
+            // Step 5: summands in the order k2,k4,k1,k3 (gpu_rodas4_perform_step.jl:213)
+            DEGK_UNROLL for (int c = 0; c < N; ++c)
+                lt[c] = -(du[c] + (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]));
+            F.solve(lt, k[4]);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[4][c];
+            Model::template f<T>(du, uu, p, t + h);
+            // Step 6: summands in the order k1,k2,k5,k4,k3 (:219)
+            { const T C61 = R4C(C61) / h, C62 = R4C(C62) / h, C63 = R4C(C63) / h, C64 = R4C(C64) / h, C65 = R4C(C65) / h;
+              DEGK_UNROLL for (int c = 0; c < N; ++c)
+                  lt[c] = -(du[c] + ((((C61 * k[0][c] + C62 * k[1][c]) + C65 * k[4][c]) + C64 * k[3][c]) + C63 * k[2][c])); }
+            F.solve(lt, k[5]);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uu[c] + k[5][c];
+        }
+        if (WANT_ERR) {
+            DEGK_UNROLL for (int c = 0; c < N; ++c) err[c] = k[NS - 1][c];
+        }
+        return true;
+    }
+
+    // interpolation vectors, formed on accept only (gpu_rodas4:245-247, gpu_rodas5P:313-323)
+    static DEGK_DEV void on_accept(Keep& K) {
+        T (&k)[NS][N] = K.ks;
+        DEGK_UNROLL for (int c = 0; c < N; ++c) {
+            if (R5) {
+                K.kk[0][c] = ((((((R5C(h21) * k[0][c] + R5C(h22) * k[1][c]) + R5C(h23) * k[2][c]) + R5C(h24) * k[3][c]) +
+                                R5C(h25) * k[4][c]) + R5C(h26) * k[5][c]) + R5C(h27) * k[NS > 6 ? 6 : 0][c]) + R5C(h28) * k[NS - 1][c];
+                K.kk[1][c] = ((((((R5C(h31) * k[0][c] + R5C(h32) * k[1][c]) + R5C(h33) * k[2][c]) + R5C(h34) * k[3][c]) +
+                                R5C(h35) * k[4][c]) + R5C(h36) * k[5][c]) + R5C(h37) * k[NS > 6 ? 6 : 0][c]) + R5C(h38) * k[NS - 1][c];
+                K.kk[2][c] = ((((((R5C(h41) * k[0][c] + R5C(h42) * k[1][c]) + R5C(h43) * k[2][c]) + R5C(h44) * k[3][c]) +
+                                R5C(h45) * k[4][c]) + R5C(h46) * k[5][c]) + R5C(h47) * k[NS > 6 ? 6 : 0][c]) + R5C(h48) * k[NS - 1][c];
+            } else {
+                K.kk[0][c] = (((R4C(h21) * k[0][c] + R4C(h22) * k[1][c]) + R4C(h23) * k[2][c]) + R4C(h24) * k[3][c]) + R4C(h25) * k[4][c];
+                K.kk[1][c] = (((R4C(h31) * k[0][c] + R4C(h32) * k[1][c]) + R4C(h33) * k[2][c]) + R4C(h34) * k[3][c]) + R4C(h35) * k[4][c];
+                K.kk[2][c] = (T)0;
+            }
+        }
+    }
+
+    // stiff/interpolants.jl:1-11 (Rodas4), :13-23 (Rodas5P)
+    static DEGK_DEV void interp(const Keep& K, T theta, T h, const T (&uprev)[N],
+                                const T (&unew)[N], const T* p, T tprev, T (&out)[N]) {
+        const T th1 = (T)1 - theta;
+        DEGK_UNROLL for (int c = 0; c < N; ++c) {
+            const T inner = R5 ? fma_(theta, fma_(theta, K.kk[2][c], K.kk[1][c]), K.kk[0][c])
+                               : fma_(theta, K.kk[1][c], K.kk[0][c]);
+            out[c] = fma_(theta, fma_(th1, inner, unew[c]), th1 * uprev[c]);
+        }
+    }
+#undef R4C
+#undef R5C
+#undef RC
+};
+
+}  // namespace degk

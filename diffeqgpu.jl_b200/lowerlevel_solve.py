@@ -1,0 +1,227 @@
+"""vectorized_solve / vectorized_asolve -- the operator boundary of the kernel path.
+
+Mirror of reference src/ensemblegpukernel/lowerlevel_solve.jl:
+    vectorized_solve(probs, prob::ODEProblem, alg; dt, saveat, save_everystep, ...)   :53-131
+    vectorized_solve(probs, prob::SDEProblem, alg; dt, saveat, save_everystep, ...)   :134-199
+    vectorized_asolve(probs, prob::ODEProblem, alg; dt, saveat, abstol, reltol, ...)  :253-346
+    vectorized_asolve(probs, prob::SDEProblem, ...) -> error                          :348-356
+Same names, argument meaning, defaults, output sizing and error behaviour; the kernel launch
+is replaced by `degk_solve` (include/degk.h).  Returns `(ts, us)` still on the device:
+ts (N, len) and us (N, len, n) torch tensors whose memory is exactly the reference's
+column-major (len x N) arrays.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .algorithms import (FP_MODES, SCHEDULES, GPUEM, GPUSIEA, GPUODEAlgorithm, GPUSDEAlgorithm)
+from .problems import ODEProblem, ProblemBatch, SDEProblem, adapt
+
+MAX_SAVEAT_LENGTH = 100_000   # lowerlevel_solve.jl:286
+
+
+class Range:
+    """start:step:stop or range(start, stop, length=n) -- stands in for Julia's AbstractRange."""
+
+    def __init__(self, start, stop, *, step=None, length=None):
+        if (step is None) == (length is None):
+            raise ValueError("give exactly one of step / length")
+        self.start, self.stop = float(start), float(stop)
+        if length is None:
+            length = int(math.floor((self.stop - self.start) / float(step) + 1e-9)) + 1
+            self.stop = self.start + (length - 1) * float(step)
+        self.length = int(length)
+
+    def collect(self, dtype):
+        # Tt.(collect(range(Tt(first), Tt(last), length = n)))  (lowerlevel_solve.jl:90-91)
+        a, b = dtype.type(self.start), dtype.type(self.stop)
+        return np.linspace(np.float64(a), np.float64(b), self.length).astype(dtype)
+
+
+def _is_number(x):
+    return isinstance(x, (int, float, np.integer, np.floating))
+
+
+def _convert_saveat_fixed(saveat, prob):
+    """lowerlevel_solve.jl:84-109 (also the SDE method :159-178)"""
+    Tt = prob.dtype
+    if isinstance(saveat, Range):
+        return saveat.collect(Tt)
+    if _is_number(saveat):
+        t0, tf = prob.tspan
+        if Tt.type(saveat) == Tt.type(0.0):
+            return np.array([t0, tf], dtype=Tt)
+        num_points = int(math.ceil(abs(tf - t0) / abs(Tt.type(saveat)))) + 1
+        return np.linspace(np.float64(t0), np.float64(tf), num_points).astype(Tt)
+    return np.asarray(saveat).astype(Tt).reshape(-1)
+
+
+def _convert_saveat_adaptive(saveat, prob):
+    """lowerlevel_solve.jl:271-306"""
+    Tt = prob.dtype
+    if _is_number(saveat):
+        t0, tf = prob.tspan
+        if Tt.type(saveat) == Tt.type(0.0):
+            return np.array([t0, tf], dtype=Tt)
+        num_points = int(math.ceil(abs(tf - t0) / abs(Tt.type(saveat)))) + 1
+        if num_points > MAX_SAVEAT_LENGTH:
+            raise ValueError(f"saveat would create too many save points ({num_points}). "
+                             "Consider using a larger saveat value.")
+        return np.linspace(np.float64(t0), np.float64(tf), num_points).astype(Tt)
+    if isinstance(saveat, Range):
+        return saveat.collect(Tt)
+    return np.asarray(saveat).astype(Tt).reshape(-1)
+
+
+def _model_key(f):
+    return (f.builtin, f.rhs, f.jac, f.tgrad, f.n_state, f.n_param, f.force_jit)
+
+
+def get_program(prob, alg, fp_mode="strict", device=None):
+    """Build (or fetch) the degk_program for (model, alg, eltype, fp mode)."""
+    ctx = _lib.context(device)
+    dtype = _lib.F32 if prob.dtype == np.float32 else _lib.F64
+    if isinstance(prob, SDEProblem):
+        sf, f = prob.f, prob.f.f
+        key = ("sde", _model_key(f), sf.g, sf.noise, sf.n_noise, alg.alg_id, dtype, fp_mode)
+        kind = {"diagonal": _lib.NOISE_DIAGONAL, "general": _lib.NOISE_GENERAL}[sf.noise]
+        desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, noise_src=sf.g, n_state=f.n_state, n_param=f.n_param,
+                              n_noise=sf.n_noise, noise_kind=kind, dtype=dtype, alg=alg.alg_id,
+                              fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit)
+    else:
+        f = prob.f
+        key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode)
+        desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, jac_src=f.jac, tgrad_src=f.tgrad,
+                              n_state=f.n_state, n_param=f.n_param, dtype=dtype, alg=alg.alg_id,
+                              fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit)
+    return ctx.program(desc, key)
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_everystep, n_rows,
+            fp_mode, schedule, layout, stats, stream, traj_offset=0, reduce=None):
+    if not isinstance(probs, ProblemBatch):
+        probs = adapt("cuda", probs)
+    dev = probs.device
+    if dev.type != "cuda":
+        raise RuntimeError("probs must live on a CUDA device: this engine has no CPU path")
+    prog = get_program(prob, alg, fp_mode, dev)
+    n = prog.info.n_state
+    N = len(probs)
+    tdt = torch.float32 if prob.dtype == np.float32 else torch.float64
+    with torch.cuda.device(dev):
+        # allocate(backend, T, (len, N)) -- lowerlevel_solve.jl:81-83 / 317-323.  ts needs no
+        # fill!(ts, t0): the kernel writes t0 into every row it does not reach.
+        if layout == "ref":
+            ts = torch.empty((N, n_rows), dtype=tdt, device=dev)
+            us = torch.empty((N, n_rows, n), dtype=tdt, device=dev)
+        else:
+            ts = torch.empty((n_rows, N), dtype=tdt, device=dev)
+            us = torch.empty((n_rows, n, N), dtype=tdt, device=dev)
+        d_saveat = None
+        if saveat is not None:
+            d_saveat = torch.as_tensor(saveat, dtype=tdt).to(dev)
+        out = {}
+        if stats:
+            out["retcode"] = torch.zeros(N, dtype=torch.int32, device=dev)
+            out["naccept"] = torch.zeros(N, dtype=torch.int32, device=dev)
+            out["nreject"] = torch.zeros(N, dtype=torch.int32, device=dev)
+            out["totals"] = torch.zeros(4, dtype=torch.int64, device=dev)
+        a = _lib.SolveArgs()
+        a.n_traj = N
+        a.traj_offset = traj_offset
+        a.u0 = _ptr(probs.u0); a.u0_stride = n if probs.u0.ndim == 2 else 0
+        a.p = _ptr(probs.p); a.p_stride = probs.p.shape[1] if probs.p.ndim == 2 else 0
+        a.tspan = _ptr(probs.tspan); a.tspan_stride = 2 if probs.tspan.ndim == 2 else 0
+        a.dt = float(prob.dtype.type(dt))
+        a.adaptive = int(adaptive)
+        a.abstol = float(prob.dtype.type(abstol)); a.reltol = float(prob.dtype.type(reltol))
+        a.saveat = _ptr(d_saveat); a.n_saveat = 0 if saveat is None else len(saveat)
+        a.save_everystep = int(bool(save_everystep))
+        a.n_rows = n_rows
+        a.us = us.data_ptr(); a.ts = ts.data_ptr()
+        a.out_layout = _lib.LAYOUT_REF if layout == "ref" else _lib.LAYOUT_SOA
+        a.schedule = SCHEDULES[schedule]
+        if stats:
+            a.retcode = out["retcode"].data_ptr(); a.naccept = out["naccept"].data_ptr()
+            a.nreject = out["nreject"].data_ptr(); a.totals = out["totals"].data_ptr()
+        a.seed = int(getattr(probs, "seed", 0)) & 0xFFFFFFFFFFFFFFFF
+        a.reduce = None if reduce is None else reduce.data_ptr()
+        a.max_iters = 0
+        s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        prog.solve(a, s)
+        # keep inputs alive until the stream has consumed them
+        us._degk_keepalive = (probs, d_saveat)
+    if stats:
+        return ts, us, out
+    return ts, us
+
+
+def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, debug=False,
+                     callback=None, tstops=None, fp_mode="strict", schedule="auto", layout="ref",
+                     stats=False, stream=None, traj_offset=0, reduce=None, **kwargs):
+    """Fixed-step batched solve; returns (ts, us) on the device (add `stats=True` for
+    per-trajectory retcode/naccept/nreject and totals, which the reference does not have)."""
+    if callback is not None or tstops is not None:
+        raise NotImplementedError("callbacks/tstops are not lowered to the C ABI yet (SURVEY §8f-2)")
+    if not isinstance(alg, GPUODEAlgorithm):
+        raise TypeError("alg must be a GPUODEAlgorithm / GPUSDEAlgorithm")
+    is_sde = isinstance(prob, SDEProblem)
+    if is_sde != isinstance(alg, GPUSDEAlgorithm):
+        raise TypeError(f"{alg!r} cannot solve a {type(prob).__name__}")
+    if is_sde and isinstance(alg, GPUSIEA) and not prob.is_diagonal_noise():
+        # lowerlevel_solve.jl:185-186
+        raise ValueError("The algorithm is not compatible with the chosen noise type. Please see "
+                         "the documentation on the solver methods")
+    Tt = prob.dtype
+    dt = Tt.type(dt)
+    dcode = _lib.F32 if Tt == np.float32 else _lib.F64
+    t0, tf = prob.tspan
+    saveat_c = None
+    if saveat is None:
+        if save_everystep:
+            # len = length(prob.tspan[1]:dt:prob.tspan[2])  (:71-73, :148-150)
+            n_rows = int(_lib.lib().degk_output_rows(dcode, float(t0), float(tf), float(dt), 0, 1, 0))
+        else:
+            n_rows = 2
+    else:
+        saveat_c = _convert_saveat_fixed(saveat, prob)
+        n_rows = len(saveat_c)
+    return _launch(probs, prob, alg, dt=dt, adaptive=False, abstol=0.0, reltol=0.0, saveat=saveat_c,
+                   save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
+                   schedule=schedule, layout=layout, stats=stats, stream=stream,
+                   traj_offset=traj_offset, reduce=reduce)
+
+
+def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save_everystep=False,
+                      abstol=np.float32(1e-6), reltol=np.float32(1e-3), debug=False, callback=None,
+                      tstops=None, fp_mode="strict", schedule="auto", layout="ref", stats=False,
+                      stream=None, **kwargs):
+    """Adaptive batched solve (defaults as lowerlevel_solve.jl:253-260)."""
+    if isinstance(prob, SDEProblem):
+        raise RuntimeError("Adaptive time-stepping is not supported yet with GPUEM.")   # :348-356
+    if callback is not None or tstops is not None:
+        raise NotImplementedError("callbacks/tstops are not lowered to the C ABI yet (SURVEY §8f-2)")
+    if not isinstance(alg, GPUODEAlgorithm) or isinstance(alg, GPUSDEAlgorithm):
+        raise TypeError("alg must be a GPUODEAlgorithm")
+    Tt = prob.dtype
+    dt = Tt.type(dt)
+    dcode = _lib.F32 if Tt == np.float32 else _lib.F64
+    t0, tf = prob.tspan
+    saveat_c = None if saveat is None else _convert_saveat_adaptive(saveat, prob)
+    if saveat_c is None:
+        # len = ceil(Int, (tf - t0)/dt) + 1 when save_everystep else 2  (:311-316).  Only the
+        # first row (+ nothing else) is ever written in the save_everystep case.
+        n_rows = int(_lib.lib().degk_output_rows(dcode, float(t0), float(tf), float(dt), 1,
+                                                 int(bool(save_everystep)), 0))
+    else:
+        n_rows = len(saveat_c)
+    return _launch(probs, prob, alg, dt=dt, adaptive=True, abstol=abstol, reltol=reltol,
+                   saveat=saveat_c, save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
+                   schedule=schedule, layout=layout, stats=stats, stream=stream)

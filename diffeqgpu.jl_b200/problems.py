@@ -1,0 +1,237 @@
+"""Problem types of the host-side mirror (the SciMLBase subset the kernel path touches).
+
+Reference: `ODEProblem`/`SDEProblem`/`EnsembleProblem` come from SciMLBase (un-vendored);
+`make_prob_compatible` is src/utils.jl:37-57; the batch `probs` handed to
+`vectorized_solve` is `adapt(dev, adapt.((dev,), probs))` (src/solve.jl:399-400), an AoS vector
+of ImmutableODEProblem.  Here the adapted batch is `ProblemBatch`: three strided device arrays
+(u0, p, tspan) -- the form the C ABI takes.
+
+The right-hand side is not a host closure: a Julia `f(u,p,t)` cannot cross a C ABI.  An
+`ODEFunction` names a built-in model or carries CUDA C++ *bodies* (what Symbolics'
+`build_function(target = CTarget())` emits) that NVRTC inlines into the stepper kernels.
+"""
+from dataclasses import dataclass, field, replace
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class ODEFunction:
+    """f(u, p, t) with optional analytic `jac` / `tgrad` (reference: SciMLBase.ODEFunction
+    with `jac =`, `tgrad =`, test/lower_level_api.jl:19-47).
+
+    builtin : name of a model compiled into libdegk, or None
+    rhs/jac/tgrad : CUDA C++ bodies writing du[i] / J[i][j] / dT[i] from u[i], p[i], t, T
+    python  : optional host callable f(u, p, t) -> du used only by tests for ground truth
+    """
+    builtin: Optional[str] = None
+    rhs: Optional[str] = None
+    jac: Optional[str] = None
+    tgrad: Optional[str] = None
+    n_state: int = 0
+    n_param: int = 0
+    python: Optional[Callable] = field(default=None, compare=False)
+    force_jit: bool = False
+
+    def __post_init__(self):
+        if self.builtin is None and self.rhs is None:
+            raise ValueError("ODEFunction needs `builtin=` or an `rhs=` source body")
+        if self.builtin is None and self.n_state <= 0:
+            raise ValueError("n_state is required for a source-defined ODEFunction")
+
+
+@dataclass(frozen=True)
+class SDEFunction:
+    """drift f and diffusion g.  noise: 'diagonal' (g[i]) or 'general' (G[i][j], n x m)."""
+    f: ODEFunction
+    g: Optional[str] = None
+    noise: str = "diagonal"
+    n_noise: int = 0
+
+
+BUILTIN_DIMS = {  # name -> (n_state, n_param, n_noise, noise_kind); mirror of degk_models.cuh
+    "lorenz": (3, 3, 3, 1), "henon_heiles": (4, 0, 0, 0), "rober": (3, 3, 0, 0),
+    "decay": (1, 1, 0, 0), "linear15": (15, 0, 0, 0), "gbm": (3, 2, 3, 1),
+    "scalar_sde": (1, 2, 1, 1), "osc_t": (2, 1, 0, 0), "gbm_nd": (2, 2, 4, 2),
+}
+
+
+def _dims(f: ODEFunction):
+    if f.builtin is not None and f.rhs is None:
+        n, npar, _, _ = BUILTIN_DIMS[f.builtin]
+        return n, npar
+    return f.n_state, f.n_param
+
+
+def _as_vec(x, dtype, n, what):
+    a = np.asarray(x, dtype=dtype).reshape(-1)
+    if a.size != n:
+        raise ValueError(f"{what} has {a.size} entries, model expects {n}")
+    return a
+
+
+@dataclass(frozen=True)
+class ODEProblem:
+    """ODEProblem{false}(f, u0::SVector, tspan, p::SVector; kwargs...).  The element type of
+    `u0` fixes T (Float32/Float64) like `eltype(prob.tspan)` does in lowerlevel_solve.jl:265."""
+    f: ODEFunction
+    u0: np.ndarray
+    tspan: tuple
+    p: Optional[np.ndarray] = None
+    kwargs: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        u0 = np.asarray(self.u0)
+        dtype = u0.dtype if u0.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+        n, npar = _dims(self.f)
+        object.__setattr__(self, "u0", _as_vec(u0, dtype, n, "u0"))
+        p = np.zeros(0, dtype) if self.p is None else np.asarray(self.p, dtype=dtype).reshape(-1)
+        if p.size != npar:
+            raise ValueError(f"p has {p.size} entries, model expects {npar}")
+        object.__setattr__(self, "p", p)
+        t0, tf = self.tspan
+        object.__setattr__(self, "tspan", (dtype.type(t0), dtype.type(tf)))
+
+    @property
+    def dtype(self):
+        return self.u0.dtype
+
+
+@dataclass(frozen=True)
+class SDEProblem:
+    """SDEProblem(f, g, u0, tspan, p; noise_rate_prototype, seed)."""
+    f: SDEFunction
+    u0: np.ndarray
+    tspan: tuple
+    p: Optional[np.ndarray] = None
+    seed: int = 0
+    kwargs: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        u0 = np.asarray(self.u0)
+        dtype = u0.dtype if u0.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+        n, npar = _dims(self.f.f)
+        object.__setattr__(self, "u0", _as_vec(u0, dtype, n, "u0"))
+        p = np.zeros(0, dtype) if self.p is None else np.asarray(self.p, dtype=dtype).reshape(-1)
+        if p.size != npar:
+            raise ValueError(f"p has {p.size} entries, model expects {npar}")
+        object.__setattr__(self, "p", p)
+        t0, tf = self.tspan
+        object.__setattr__(self, "tspan", (dtype.type(t0), dtype.type(tf)))
+
+    @property
+    def dtype(self):
+        return self.u0.dtype
+
+    def is_diagonal_noise(self):
+        if self.f.g is None and self.f.f.builtin is not None:
+            return BUILTIN_DIMS[self.f.f.builtin][3] == 1
+        return self.f.noise == "diagonal"
+
+
+def remake(prob, **changes):
+    """SciMLBase.remake: copy with some fields replaced."""
+    return replace(prob, **changes)
+
+
+def make_prob_compatible(prob):
+    """reference src/utils.jl:37-57: ODEProblem -> ImmutableODEProblem.  Problems here are
+    already immutable value types with static-size state; returned unchanged."""
+    return prob
+
+
+@dataclass
+class EnsembleProblem:
+    """SciMLBase.EnsembleProblem(prob; prob_func, output_func, reduction, u_init, safetycopy).
+    prob_func(prob, ctx) -> prob where ctx has `.sim_id` (1-based, like the reference's
+    `_make_ensemble_context(i, ...)`, src/solve.jl:187-202)."""
+    prob: object
+    prob_func: Optional[Callable] = None
+    output_func: Optional[Callable] = None
+    reduction: Optional[Callable] = None
+    u_init: object = None
+    safetycopy: bool = True
+
+
+@dataclass(frozen=True)
+class EnsembleContext:
+    sim_id: int
+    sim_seed: Optional[int] = None
+
+
+class ProblemBatch:
+    """`probs` adapted to the device: u0 (N, n), p (N, np) and tspan ((2,) shared or (N, 2))
+    as torch CUDA tensors.  Reference: `adapt(dev, adapt.((dev,), probs))`, src/solve.jl:399-400.
+    """
+
+    def __init__(self, prob, u0, p, tspan, n_traj, seed=0):
+        self.prob = prob
+        self.u0, self.p, self.tspan = u0, p, tspan
+        self.n_traj = int(n_traj)
+        self.seed = int(seed)
+
+    def __len__(self):
+        return self.n_traj
+
+    @property
+    def device(self):
+        return self.u0.device
+
+    @staticmethod
+    def from_arrays(prob, *, u0=None, p=None, tspan=None, n_traj=None, device="cuda", seed=None):
+        """Build a batch directly from arrays (no per-trajectory Python objects).
+        Each of u0/p/tspan may be None (use the prototype's value, broadcast) or an array with
+        a leading trajectory axis."""
+        dt = torch.float32 if prob.dtype == np.float32 else torch.float64
+        dev = torch.device(device)
+
+        def conv(x, proto, width):
+            if x is None:
+                return torch.as_tensor(np.asarray(proto), dtype=dt).reshape(-1).to(dev)
+            if not isinstance(x, torch.Tensor):
+                x = torch.as_tensor(np.ascontiguousarray(x))
+            x = x.to(device=dev, dtype=dt).contiguous()
+            if x.ndim == 1 and x.numel() == width:
+                return x
+            if x.ndim != 2 or x.shape[1] != width:
+                raise ValueError(f"expected shape (N, {width}), got {tuple(x.shape)}")
+            return x
+
+        n = prob.u0.size
+        u0_t = conv(u0, prob.u0, n)
+        p_t = conv(p, prob.p, prob.p.size) if prob.p.size else torch.zeros(0, dtype=dt, device=dev)
+        ts_t = conv(tspan, prob.tspan, 2)
+        sizes = [t.shape[0] for t in (u0_t, p_t, ts_t) if t.ndim == 2]
+        if n_traj is None:
+            if not sizes:
+                raise ValueError("n_traj is required when every input is broadcast")
+            n_traj = sizes[0]
+        if any(s != n_traj for s in sizes):
+            raise ValueError("u0/p/tspan disagree on the number of trajectories")
+        if seed is None:
+            seed = getattr(prob, "seed", 0)
+        return ProblemBatch(prob, u0_t, p_t, ts_t, n_traj, seed)
+
+    @staticmethod
+    def from_problems(probs: Sequence, device="cuda"):
+        """AoS list of problems -> SoA-per-field batch (host loop #1 of src/solve.jl:187-202)."""
+        if len(probs) == 0:
+            raise ValueError("empty batch")
+        proto = probs[0]
+        u0 = np.stack([pr.u0 for pr in probs])
+        p = np.stack([pr.p for pr in probs]) if proto.p.size else None
+        ts = np.array([pr.tspan for pr in probs], dtype=proto.dtype)
+        same_t = bool((ts == ts[0]).all())
+        return ProblemBatch.from_arrays(proto, u0=u0, p=p, tspan=None if same_t else ts,
+                                        n_traj=len(probs), device=device)
+
+
+def adapt(device, probs):
+    """reference: adapt(dev, probs)"""
+    if isinstance(probs, ProblemBatch):
+        return probs
+    return ProblemBatch.from_problems(list(probs), device=device)

@@ -1,0 +1,47 @@
+"""Seeded inputs shared by the oracle tests, the golden-vector generator and the GPU parity tests."""
+import numpy as np
+
+P0_LORENZ = np.array([10.0, 28.0, 8.0 / 3.0])
+K0_ROBER = np.array([0.04, 3.0e7, 1.0e4])
+
+
+def lorenz_sweep(n, dtype=np.float32, seed=20240607):
+    """p_i = r_i .* (10, 28, 8/3), r ~ U[0,1)^3 in Float32 (README.md:74 of the reference)"""
+    r = np.random.default_rng(seed).random((n, 3), dtype=np.float32)
+    return (r * P0_LORENZ.astype(np.float32)).astype(dtype)
+
+
+def rober_sweep(n, dtype=np.float32, seed=7):
+    r = np.random.default_rng(seed).random((n, 3))
+    return (K0_ROBER * (0.5 + r)).astype(dtype)
+
+
+def henon_heiles_u0(n, dtype=np.float64, seed=11):
+    """E = 1/8, x = 0, y = -0.1 + 0.3 r1, py = -0.1 + 0.2 r2"""
+    r = np.random.default_rng(seed).random((n, 2))
+    y = -0.1 + 0.3 * r[:, 0]
+    py = -0.1 + 0.2 * r[:, 1]
+    px = np.sqrt(2 * 0.125 - py ** 2 - y ** 2 + (2.0 / 3.0) * y ** 3)
+    return np.stack([np.zeros(n), y, px, py], axis=1).astype(dtype)
+
+
+U0_LORENZ = np.array([1.0, 0.0, 0.0])
+
+# (name, kwargs for oracle.solve) -- small cases whose oracle outputs are committed as goldens
+def golden_cases():
+    f32, f64 = np.float32, np.float64
+    sv = np.arange(0, 11.0)
+    cases = []
+    for alg in ("tsit5", "vern7", "vern9"):
+        cases.append((f"lorenz_{alg}_fixed_f32", dict(model="lorenz", alg=alg, u0=U0_LORENZ, p=lorenz_sweep(16), tspan=[0, 10], dt=0.1, length=101, dtype=f32)))
+        cases.append((f"lorenz_{alg}_adaptive_saveat_f32", dict(model="lorenz", alg=alg, u0=U0_LORENZ, p=lorenz_sweep(16), tspan=[0, 10], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, saveat=sv, dtype=f32)))
+        cases.append((f"lorenz_{alg}_adaptive_endpoints_f64", dict(model="lorenz", alg=alg, u0=U0_LORENZ, p=lorenz_sweep(16, f64), tspan=[0, 10], dt=0.1, adaptive=True, abstol=1e-10, reltol=1e-10, save_everystep=False, dtype=f64)))
+    cases.append(("hh_vern9_adaptive_f64", dict(model="henon_heiles", alg="vern9", u0=henon_heiles_u0(16), p=None, tspan=[0, 100], dt=0.1, adaptive=True, abstol=1e-10, reltol=1e-10, save_everystep=False, dtype=f64)))
+    for alg in ("rosenbrock23", "rodas4", "rodas5p"):
+        cases.append((f"rober_{alg}_adaptive_f32", dict(model="rober", alg=alg, u0=U0_LORENZ, p=rober_sweep(16), tspan=[0, 1e5], dt=1e-4, adaptive=True, abstol=1e-8, reltol=1e-4, saveat=[1.0, 10.0, 1e3, 1e5], dtype=f32)))
+        cases.append((f"decay_{alg}_fixed_f32", dict(model="decay", alg=alg, u0=[10.0], p=[1.0], tspan=[0, 10], dt=0.01, length=1001, dtype=f32)))
+        cases.append((f"lorenz_{alg}_adaptive_f64", dict(model="lorenz", alg=alg, u0=U0_LORENZ, p=lorenz_sweep(8, f64), tspan=[0, 2], dt=0.01, adaptive=True, abstol=1e-8, reltol=1e-8, saveat=[0.5, 1.0, 2.0], dtype=f64)))
+    for alg in ("em", "siea"):
+        cases.append((f"gbm_{alg}_f32", dict(model="gbm", alg=alg, u0=np.full((32, 3), 0.1), p=[1.5, 0.01], tspan=[0, 1], dt=1 / 64, save_everystep=False, seed=1234, dtype=f32)))
+    cases.append(("lorenz_additive_em_saveat_f32", dict(model="lorenz_additive", alg="em", u0=U0_LORENZ, p=lorenz_sweep(8), tspan=[0, 1], dt=1e-3, saveat=[0.0, 0.25, 0.5, 1.0], seed=7, dtype=f32)))
+    return cases
