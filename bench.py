@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): Lorenz GPUTsit5 adaptive,
+abstol = reltol = 1e-6, saveat 0:1:10, Float32, random parameter sweep (config C2).
+
+    python bench.py --gpus N --steps K --warmup W            # our engine
+    python bench.py --impl reference --gpus N ...            # the reference algorithm's CPU path
+
+One "step" = one complete batched solve of `--traj` trajectories per GPU (weak scaling:
+trajectories shard by index range, no data-path collective).  Prints ONE JSON line:
+  value  = attempted trajectory-steps / s over all GPUs, inputs resident in HBM, CUDA-event timed
+  e2e    = same metric through degk_solve_host with HOST buffers (H2D of the problems, solve,
+           D2H of ts/us inside the timed region)
+  roofline = algorithmic FLOPs (263 per attempted step) / kernel time against the
+           FP32 FMA issue peak measured in this run (FFMA micro-kernel; MEASURED_PEAKS.json holds
+           only HBM and tensor peaks, and this path is FMA-bound), plus the HBM view
+  cpu_baseline = the CPU oracle (a port of the reference's per-trajectory algorithm) on the
+           host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+F_ALG = 263.0          # algorithmic flops per attempted Tsit5 step on Lorenz (67n+14+6F, n=3, F=8)
+BYTES_IN = 12.0        # per trajectory: p (3 x f32); u0 and tspan are broadcast
+BYTES_OUT = 176.0      # per trajectory: us 11 x 3 x 4 + ts 11 x 4
+METRIC = "Lorenz GPUTsit5 adaptive trajectory-steps/s (abstol=reltol=1e-6, saveat 0:1:10, Float32)"
+P0 = np.array([10.0, 28.0, 8.0 / 3.0], np.float32)
+U0 = np.array([1.0, 0.0, 0.0], np.float32)
+SAVEAT = np.arange(0, 11, dtype=np.float32)
+
+
+def workload_name(traj):
+    return f"C2: Lorenz GPUTsit5 adaptive tol 1e-6, saveat 0:1:10, f32, {traj} trajectories/GPU, p = U[0,1)^3 .* (10,28,8/3)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU path.  Julia is not installed on the box,
+    so this is the oracle port (oracle/degk_oracle.cpp, OpenMP over trajectories, all host
+    threads) on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    n = args.ref_traj
+    rng = np.random.default_rng(0)
+    times, steps = [], 0
+    for i in range(args.warmup + args.steps):
+        p = rng.random((n, 3), dtype=np.float32) * P0
+        t0 = time.perf_counter()
+        r = oracle.solve("lorenz", "tsit5", U0, p, [0, 10], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6,
+                         saveat=SAVEAT, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            steps += int(r["naccept"].sum() + r["nreject"].sum())
+    value = steps / sum(times)
+    sample = f"{n} trajectories per step of the C2 workload (of {args.traj} per GPU in the GPU arm)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "trajectory-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.traj), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def measure_fma_peak(torch, dev):
+    """FP32 FMA issue peak of this GPU right now: tools/fma_peak.cu built into libdegk would be
+    circular, so use the standalone micro-benchmark binary if present."""
+    exe = ROOT / "tools" / "bin" / "fma_peak"
+    if exe.exists():
+        try:
+            out = subprocess.check_output([str(exe)], env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(dev)), text=True, timeout=60)
+            return json.loads(out.strip().splitlines()[-1])
+        except Exception:
+            pass
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="degk", choices=["degk", "reference"])
+    ap.add_argument("--traj", type=int, default=int(os.environ.get("DEGK_BENCH_TRAJ", 100_000_000)),
+                    help="trajectories per GPU (weak scaling)")
+    ap.add_argument("--fp", default=os.environ.get("DEGK_BENCH_FP", "fast"), choices=["fast", "strict"])
+    ap.add_argument("--schedule", default="queue", choices=["queue", "static"])
+    ap.add_argument("--ref-traj", type=int, default=1_000_000)
+    ap.add_argument("--cpu-traj", type=int, default=400_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import diffeqgpu_b200 as dg
+    from diffeqgpu_b200.parallel import init_from_env, max_over_ranks, sum_over_ranks
+    import torch.distributed as dist
+
+    rank, local, world = init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    N = args.traj
+    f32 = np.float32
+
+    # ---- synthetic inputs, generated on the device (resident in HBM before timing) ----
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    p = torch.rand((N, 3), generator=gen, device=dev, dtype=torch.float32) * torch.tensor(P0, device=dev)
+    prob = dg.ODEProblem(dg.models.lorenz, U0, (0.0, 10.0), P0)
+    probs = dg.ProblemBatch.from_arrays(prob, p=p, device=dev)
+    alg = dg.GPUTsit5()
+    kw = dict(dt=f32(0.1), saveat=SAVEAT, abstol=f32(1e-6), reltol=f32(1e-6), fp_mode=args.fp,
+              schedule=args.schedule, stats=True)
+    info = dg.get_program(prob, alg, args.fp, dev).info
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # one solve outside timing to size things and obtain the attempted-step count
+    ts, us, st = dg.vectorized_asolve(probs, prob, alg, **kw)
+    torch.cuda.synchronize(dev)
+    tot = st["totals"].cpu().numpy().astype(np.int64)
+    attempts_per_step = int(tot[0] + tot[1])
+    accepted_per_step = int(tot[0])
+    assert int(tot[2]) == 0, "failed trajectories in the benchmark workload"
+    assert bool((ts[:: max(1, N // 1000)] == torch.tensor(SAVEAT, device=dev)).all())
+    del ts, us, st
+
+    for _ in range(args.warmup):
+        out = dg.vectorized_asolve(probs, prob, alg, **kw)
+        del out
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        out = dg.vectorized_asolve(probs, prob, alg, **kw)
+        a1.record()
+        kernel_ms.append((a0, a1))
+        del out
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ms]))
+    total_attempts = sum_over_ranks(attempts_per_step, dev) * args.steps
+    value = total_attempts / (ms_total * 1e-3)
+
+    # ---- the bit-parity build (strict fp) on the same inputs, for reference next to `value` ----
+    other = None
+    if args.fp == "fast":
+        kws = dict(kw, fp_mode="strict")
+        out = dg.vectorized_asolve(probs, prob, alg, **kws)
+        tot_s = out[2]["totals"].cpu().numpy().astype(np.int64)
+        del out
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(2):
+            out = dg.vectorized_asolve(probs, prob, alg, **kws)
+            del out
+        s1.record()
+        barrier()
+        ms_s = max_over_ranks(s0.elapsed_time(s1), dev)
+        other = {"fp_mode": "strict", "value": sum_over_ranks(int(tot_s[0] + tot_s[1]), dev) * 2 / (ms_s * 1e-3),
+                 "ms_per_step": ms_s / 2, "note": "bit-identical to the oracle (un-fused FMUL/FADD like the reference)"}
+
+    # ---- end to end: host buffers through degk_solve_host ----
+    e2e = None
+    if not args.no_e2e:
+        cap = int(100e9 / world / (BYTES_OUT + BYTES_IN))
+        Ne = min(N, cap)
+        p_host = torch.empty((Ne, 3), dtype=torch.float32, pin_memory=True)
+        p_host.copy_(p[:Ne])
+        us_h = torch.empty((Ne, 11, 3), dtype=torch.float32, pin_memory=True)
+        ts_h = torch.empty((Ne, 11), dtype=torch.float32, pin_memory=True)
+        hk = dict(p=p_host, dt=f32(0.1), adaptive=True, abstol=1e-6, reltol=1e-6, saveat=SAVEAT, fp_mode=args.fp,
+                  schedule=args.schedule, out={"us": us_h, "ts": ts_h}, stats=True, device=dev, chunk_traj=1 << 22)
+        _, _, hst = dg.solve_host(prob, alg, **hk)        # warm-up (allocates workspaces)
+        att_e = int(hst["totals"][0] + hst["totals"][1])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            dg.solve_host(prob, alg, **hk)
+        torch.cuda.synchronize(dev)
+        t_e = max_over_ranks(time.perf_counter() - t0, dev)
+        tot_e = sum_over_ranks(att_e, dev) * args.e2e_steps
+        e2e = {"value": tot_e / t_e, "unit": "trajectory-steps/s", "h2d_bytes_per_step": int(Ne * BYTES_IN + 44 + 20),
+               "d2h_bytes_per_step": int(Ne * BYTES_OUT), "traj_per_gpu": Ne, "ms_per_step": 1e3 * t_e / args.e2e_steps,
+               "note": "degk_solve_host: pinned host buffers, 4M-trajectory chunks over 3 streams; timed with the host clock around the blocking call, max over ranks"}
+        del p_host, us_h, ts_h
+
+    if rank != 0:
+        return
+    # ---- roofline (rank 0's kernel) ----
+    peaks = {}
+    mp = ROOT / "MEASURED_PEAKS.json"
+    if mp.exists():
+        peaks = json.loads(mp.read_text())
+    fma = measure_fma_peak(torch, local)
+    if fma:
+        fma_peak, peak_src = fma["ffma_imm_tflops"], "measured in this run (tools/fma_peak.cu, FFMA imm-form burst)"
+    else:
+        fma_peak, peak_src = 2 * 128 * 148 * 1.965e9 / 1e12, "nominal 148 SM x 128 FMA/clk x 1.965 GHz (micro-benchmark binary missing)"
+    achieved = F_ALG * attempts_per_step / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tj = ROOT / "profiles" / "c2_dram_traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text())
+        traffic = t.get("bytes_per_trajectory", 0) * N
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_ach = (BYTES_IN + BYTES_OUT) * N / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_ode_asolve<float, Lorenz, ErkTsit5>",
+                "kernel_ms": k_ms, "flops_per_attempt": F_ALG,
+                "hbm_view": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
+    # ---- CPU baseline (oracle port, bounded sample) ----
+    cpu = None
+    try:
+        from oracle import oracle
+        cores = os.cpu_count() or 1
+        ps = (np.random.default_rng(0).random((args.cpu_traj, 3), dtype=np.float32) * P0)
+        t0 = time.perf_counter()
+        r = oracle.solve("lorenz", "tsit5", U0, ps, [0, 10], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6,
+                         saveat=SAVEAT, nthreads=cores)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": float(r["naccept"].sum() + r["nreject"].sum()) / dtc, "unit": "trajectory-steps/s",
+               "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_traj} trajectories of the same workload, oracle/degk_oracle.cpp with OpenMP"}
+    except Exception as ex:   # the oracle is test infrastructure; the bench line survives without it
+        cpu = {"value": None, "unit": "trajectory-steps/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "trajectory-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(N), "fp_mode": args.fp, "schedule": args.schedule,
+                   "l2": "inputs (1.2 GB of parameters) and outputs (17.6 GB) exceed the 126 MB L2; no flush needed",
+                   "attempted_steps_per_step": attempts_per_step, "accepted_steps_per_step": accepted_per_step,
+                   "regs_per_thread": info.regs_adaptive, "blocks_per_sm": info.max_blocks_per_sm},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "strict_fp": other,
+        "roofline": roofline, "cpu_baseline": cpu,
+    }))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,42 @@
+// degk_pack.cuh -- Pk2: two Float32 trajectories packed in one 64-bit register pair.
+//
+// Blackwell (sm_100) adds packed FP32 arithmetic: one FFMA2 / FMUL2 / FADD2 instruction performs
+// the operation on both halves of a register pair (PTX fma/mul/add.f32x2).  The FMA pipe
+// throughput in FLOP/s is unchanged, but the ISSUE cost per FLOP halves, which is what bounds
+// this engine (SASS of the ensemble kernels is issue-bound, not pipe-bound: see DESIGN.md).
+// Instantiating the generated stage code and the model RHS with T = Pk2 therefore advances two
+// trajectories per thread with half the instructions per trajectory.
+//
+// ptxas fuses mul.f32x2 + add.f32x2 into FFMA2 whenever the product has a single use, and it
+// does so even under --fmad=false and for .rn-qualified operands (checked with CUDA 12.9:
+// cuobjdump shows FFMA2 for `mul.rn.f32x2; add.rn.f32x2`).  Un-fused bit-parity arithmetic can
+// therefore not be expressed with packed operations, so Pk2 is used by the fast fp mode only;
+// the strict mode stays scalar.
+#pragma once
+#include "degk_common.cuh"
+
+namespace degk {
+
+struct Pk2 {
+    unsigned long long v;
+    DEGK_DEV Pk2() {}
+    DEGK_DEV Pk2(float a, float b) { asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b)); }
+    DEGK_DEV explicit Pk2(float a) { asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(a)); }
+    DEGK_DEV explicit Pk2(double a) { const float f = (float)a; asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(f)); }
+    DEGK_DEV explicit Pk2(int a) { const float f = (float)a; asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(f)); }
+    DEGK_DEV float lo() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+    DEGK_DEV float hi() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+    DEGK_DEV float get(int s) const { return s ? hi() : lo(); }
+};
+
+DEGK_DEV Pk2 operator*(Pk2 a, Pk2 b) { Pk2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEGK_DEV Pk2 operator+(Pk2 a, Pk2 b) { Pk2 r; asm("add.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEGK_DEV Pk2 operator-(Pk2 a, Pk2 b) { Pk2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+DEGK_DEV Pk2 operator-(Pk2 a) { Pk2 r; r.v = a.v ^ 0x8000000080000000ull; return r; }
+DEGK_DEV Pk2 fma_(Pk2 a, Pk2 b, Pk2 c) {
+    Pk2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r;
+}
+// per-half select: s0 ? a.lo : b.lo , s1 ? a.hi : b.hi
+DEGK_DEV Pk2 select2(bool s0, bool s1, Pk2 a, Pk2 b) { return Pk2(s0 ? a.lo() : b.lo(), s1 ? a.hi() : b.hi()); }
+
+}  // namespace degk
