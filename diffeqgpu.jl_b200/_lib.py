@@ -18,6 +18,7 @@ FP_STRICT, FP_FAST = 0, 1
 LAYOUT_REF, LAYOUT_SOA = 0, 1
 SCHED_STATIC, SCHED_QUEUE, SCHED_AUTO = 0, 1, 2
 NOISE_NONE, NOISE_DIAGONAL, NOISE_GENERAL = 0, 1, 2
+ENGINE_AUTO, ENGINE_V1 = 0, 1
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
             5: "Singular"}
 
@@ -42,7 +43,10 @@ class ProgramInfo(C.Structure):
                 ("fp_mode", C.c_int32), ("is_jit", C.c_int32),
                 ("regs_fixed", C.c_int32), ("regs_adaptive", C.c_int32),
                 ("local_bytes_fixed", C.c_int32), ("local_bytes_adaptive", C.c_int32),
-                ("max_blocks_per_sm", C.c_int32), ("jit_seconds", C.c_double)]
+                ("max_blocks_per_sm", C.c_int32),
+                ("regs_adaptive2", C.c_int32), ("local_bytes_adaptive2", C.c_int32),
+                ("slots_per_thread2", C.c_int32), ("max_blocks_per_sm2", C.c_int32),
+                ("jit_seconds", C.c_double)]
 
 
 class SolveArgs(C.Structure):
@@ -57,7 +61,7 @@ class SolveArgs(C.Structure):
                 ("out_layout", C.c_int32), ("schedule", C.c_int32),
                 ("retcode", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p),
                 ("seed", C.c_uint64), ("reduce", C.c_void_p), ("totals", C.c_void_p),
-                ("max_iters", C.c_int64)]
+                ("max_iters", C.c_int64), ("engine", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/degk.h declares (checked by tests/test_abi.py)

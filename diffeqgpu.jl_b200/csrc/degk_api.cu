@@ -185,6 +185,10 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
         } else {
             prog->fn[0] = e0->fn;
             prog->fn[1] = e1 ? e1->fn : nullptr;
+            if (e1 && e1->fn2) {
+                prog->fn[2] = e1->fn2;
+                prog->w2 = e1->w2; prog->qcap2 = e1->qcap2; prog->rec_bytes2 = e1->rec_bytes2;
+            }
             prog->info.n_state = e0->n_state; prog->info.n_param = e0->n_param;
             prog->info.n_noise = e0->n_noise; prog->info.noise_kind = e0->noise_kind;
             for (int k = 0; k < 2; ++k) {
@@ -204,6 +208,16 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
             const void* fo = prog->fn[1] ? prog->fn[1] : prog->fn[0];
             CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fo, DEGK_BLOCK, 0));
             prog->info.max_blocks_per_sm = occ;
+            if (prog->fn[2]) {
+                cudaFuncAttributes fa;
+                CK(ctx, cudaFuncGetAttributes(&fa, prog->fn[2]));
+                prog->info.regs_adaptive2 = fa.numRegs;
+                prog->info.local_bytes_adaptive2 = (int)fa.localSizeBytes;
+                prog->info.slots_per_thread2 = prog->w2;
+                const size_t smem = (size_t)(DEGK_BLOCK2 / 32) * prog->qcap2 * prog->rec_bytes2 + 1024 * dtype_size(d->dtype);
+                CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prog->fn[2], DEGK_BLOCK2, smem));
+                prog->info.max_blocks_per_sm2 = occ;
+            }
         }
     }
     if (!use_aot) {
@@ -349,9 +363,18 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     if (!which) sched = DEGK_SCHED_STATIC;
     k.schedule = sched;
 
-    long long blocks = (a->n_traj + DEGK_BLOCK - 1) / DEGK_BLOCK;
+    // second-generation adaptive kernel (deferred saves, packed pairs) unless the caller pins v1
+    const bool v2 = which == 1 && a->engine != DEGK_ENGINE_V1 && prog->info.slots_per_thread2 > 0;
+    const int block = v2 ? DEGK_BLOCK2 : DEGK_BLOCK;
+    const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : DEGK_BLOCK;
+    size_t smem = 0;
+    if (v2) {
+        const int nsv = (a->saveat && a->n_saveat <= 1024) ? a->n_saveat : 0;
+        smem = (size_t)(DEGK_BLOCK2 / 32) * prog->qcap2 * prog->rec_bytes2 + (size_t)nsv * dtype_size(prog->info.dtype);
+    }
+    long long blocks = (a->n_traj + per_block - 1) / per_block;
     if (sched == DEGK_SCHED_QUEUE) {
-        long long resident = (long long)ctx->sm_count * std::max(1, prog->info.max_blocks_per_sm);
+        long long resident = (long long)ctx->sm_count * std::max(1, v2 ? prog->info.max_blocks_per_sm2 : prog->info.max_blocks_per_sm);
         if (blocks > resident) blocks = resident;
         unsigned slot = ctx->next_counter.fetch_add(1) % DEGK_NCOUNTERS;
         k.work_counter = ctx->d_counters + slot;
@@ -359,9 +382,10 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     }
     if (blocks > 2147483647LL) { degk_set_error(ctx, "too many blocks"); return DEGK_ERR_INVALID; }
 
-    if (prog->info.is_jit) return degk_jit_launch(prog, which, (unsigned)blocks, DEGK_BLOCK, &k, stream);
+    const int kidx = v2 ? 2 : which;
+    if (prog->info.is_jit) return degk_jit_launch(prog, kidx, (unsigned)blocks, (unsigned)block, (unsigned)smem, &k, stream);
     void* params[1] = {(void*)&k};
-    CK(ctx, cudaLaunchKernel(prog->fn[which], dim3((unsigned)blocks), dim3(DEGK_BLOCK), params, 0, stream));
+    CK(ctx, cudaLaunchKernel(prog->fn[kidx], dim3((unsigned)blocks), dim3((unsigned)block), params, smem, stream));
     return DEGK_OK;
 }
 

@@ -33,15 +33,16 @@ struct degk_program {
     degk_ctx* ctx = nullptr;
     degk_program_info info;
     bool is_sde = false;
-    const void* fn[2] = {nullptr, nullptr};   // AOT kernels: [0] fixed-dt / SDE, [1] adaptive
+    const void* fn[3] = {nullptr, nullptr, nullptr};   // AOT kernels: [0] fixed-dt / SDE, [1] adaptive v1, [2] adaptive v2
+    int w2 = 0, qcap2 = 0, rec_bytes2 = 0;             // geometry of the v2 kernel (see degk_internal.h)
     void* jit_module = nullptr;               // CUmodule
-    void* jit_fn[2] = {nullptr, nullptr};     // CUfunction
+    void* jit_fn[3] = {nullptr, nullptr, nullptr};     // CUfunction, same indexing as fn
 };
 
 void degk_set_error(degk_ctx* ctx, const char* fmt, ...);
 
 // NVRTC path (degk_jit.cpp)
 int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog);
-int degk_jit_launch(degk_program* prog, int which, unsigned grid, unsigned block,
+int degk_jit_launch(degk_program* prog, int which, unsigned grid, unsigned block, unsigned smem,
                     const degk::KArgs* args, cudaStream_t stream);
 void degk_jit_release(degk_program* prog);

@@ -1,7 +1,8 @@
 // degk_internal.h -- definitions shared by the host-side translation units of libdegk.
 #pragma once
 
-#define DEGK_BLOCK 256   // threads per block of every stepper kernel (__launch_bounds__)
+#define DEGK_BLOCK 256    // threads per block of the first-generation kernels (__launch_bounds__)
+#define DEGK_BLOCK2 128   // threads per block of the second-generation adaptive kernel
 
 struct degk_aot_entry {
     const char* model;
@@ -10,4 +11,9 @@ struct degk_aot_entry {
     int adaptive;   // 0 fixed-dt (and SDE), 1 adaptive
     int n_state, n_param, n_noise, noise_kind;
     const void* fn; // __global__ kernel taking (const degk::KArgs)
+    // second-generation adaptive kernel (deferred saves, optionally packed pairs); null if none
+    const void* fn2;
+    int w2;         // trajectories per thread of fn2 (1 or 2)
+    int qcap2;      // save-queue capacity per warp (records)
+    int rec_bytes2; // sizeof(SaveRec<T, N>)
 };

@@ -127,6 +127,28 @@ const char* method_type(int alg) {
     default: return "";
     }
 }
+const char* method_template(int alg) {
+    switch (alg) {
+    case DEGK_ALG_TSIT5: return "degk::ErkTsit5<T_, M_>";
+    case DEGK_ALG_VERN7: return "degk::ErkVern7<T_, M_>";
+    case DEGK_ALG_VERN9: return "degk::ErkVern9<T_, M_>";
+    case DEGK_ALG_ROSENBROCK23: return "degk::Rosenbrock23<T_, M_>";
+    case DEGK_ALG_RODAS4: return "degk::Rodas<T_, M_, false>";
+    case DEGK_ALG_RODAS5P: return "degk::Rodas<T_, M_, true>";
+    default: return "";
+    }
+}
+int builtin_n_state(const char* name) {
+    static const struct { const char* n; int N; } dims[] = {{"lorenz", 3}, {"henon_heiles", 4}, {"rober", 3}, {"decay", 1},
+        {"linear15", 15}, {"gbm", 3}, {"scalar_sde", 1}, {"osc_t", 2}, {"gbm_nd", 2}};
+    for (auto& m : dims) if (name && strcmp(m.n, name) == 0) return m.N;
+    return 0;
+}
+// packed pairs (2 trajectories per thread) for Float32 explicit RK in fast mode; a model whose
+// body does not compile for the packed type (e.g. it calls cos()) falls back to 1 slot
+int default_slots(const degk_model_desc* d) {
+    return (d->dtype == DEGK_F32 && d->fp_mode == DEGK_FP_FAST && d->alg <= DEGK_ALG_VERN9) ? 2 : 1;
+}
 const char* builtin_struct(const char* name) {
     static const char* map[][2] = {{"lorenz", "Lorenz"}, {"henon_heiles", "HenonHeiles"}, {"rober", "Rober"},
                                    {"decay", "Decay"}, {"linear15", "Linear15"}, {"gbm", "Gbm"},
@@ -138,13 +160,24 @@ const char* builtin_struct(const char* name) {
 }  // namespace
 
 // Build the translation unit handed to NVRTC.
-static int make_source(degk_ctx* ctx, const degk_model_desc* d, std::string& src) {
+// host-side mirror of sizeof(degk::SaveRec<T, N>) (checked by a static_assert in the JIT source)
+static int save_rec_bytes(int dtype, int n_state) {
+    const int es = dtype == DEGK_F64 ? 8 : 4;
+    int b = 8 + 4;                       // traj, cur
+    if (es == 8) b += 4;                 // padding before the first double
+    b += 3 * es + n_state * es;          // tprev, h, tnew, u[N]
+    return (b + 15) / 16 * 16;           // __align__(16)
+}
+
+// `slots` = trajectories per thread of the second-generation adaptive kernel (1 or 2)
+static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::string& src) {
     const bool is_sde = d->alg == DEGK_ALG_EM || d->alg == DEGK_ALG_SIEA;
     const bool stiff = d->alg >= DEGK_ALG_ROSENBROCK23 && d->alg <= DEGK_ALG_RODAS5P;
     char buf[512];
-    src += "#include \"degk_common.cuh\"\n";
+    src += "#include \"degk_common.cuh\"\n#include \"degk_pack.cuh\"\n";
     src += std::string("#include \"") + method_header(d->alg) + "\"\n";
-    src += is_sde ? "#include \"degk_sde_kernels.cuh\"\n" : "#include \"degk_ode_kernels.cuh\"\n";
+    src += is_sde ? "#include \"degk_sde_kernels.cuh\"\n"
+                  : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels2.cuh\"\n";
     snprintf(buf, sizeof buf, "typedef %s REAL;\n", d->dtype == DEGK_F64 ? "double" : "float");
     src += buf;
     if (d->rhs_src) {
@@ -207,17 +240,24 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, std::string& src
         src += buf;
     } else {
         src += std::string("typedef ") + method_type(d->alg) + " METHOD;\n";
+        src += std::string("template <class T_, class M_> using METHODT = ") + method_template(d->alg) + ";\n";
         src += "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
                "    degk::ode_solve_body<REAL, MODEL, METHOD>(a);\n}\n"
                "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_adaptive(const degk::KArgs a) {\n"
                "    degk::ode_asolve_body<REAL, MODEL, METHOD>(a);\n}\n";
+        snprintf(buf, sizeof buf,
+                 "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
+                 "extern \"C\" __global__ void __launch_bounds__(%d) degk_jit_adaptive2(const degk::KArgs a) {\n"
+                 "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
+                 "    degk::ode_asolve2_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
+                 save_rec_bytes(d->dtype, d->rhs_src ? d->n_state : builtin_n_state(d->builtin)), DEGK_BLOCK2, slots);
+        src += buf;
     }
-    src += "extern \"C\" __device__ const int degk_jit_dims[4] = {MODEL::N, MODEL::NP, MODEL::M, MODEL::NOISE};\n";
     return DEGK_OK;
 }
 
 // Compile to a cubin.  Usable without a GPU (NVRTC is a pure compiler).
-static int compile_cubin(degk_ctx* ctx, const degk_model_desc* d, std::vector<char>& cubin,
+static int compile_cubin(degk_ctx* ctx, const degk_model_desc* d, int slots, std::vector<char>& cubin,
                          std::string& log) {
     std::call_once(g_nvrtc_once, load_nvrtc);
     if (!g_nvrtc.h) {
@@ -225,7 +265,7 @@ static int compile_cubin(degk_ctx* ctx, const degk_model_desc* d, std::vector<ch
         return DEGK_ERR_NVRTC;
     }
     std::string src;
-    int rc = make_source(ctx, d, src);
+    int rc = make_source(ctx, d, slots, src);
     if (rc != DEGK_OK) return rc;
     nvrtcProgram prog = nullptr;
     int e = g_nvrtc.CreateProgram(&prog, src.c_str(), "degk_jit.cu", degk_embedded_count,
@@ -255,7 +295,9 @@ extern "C" int degk_jit_compile_check(const degk_model_desc* d, int64_t* cubin_b
     std::vector<char> cubin;
     std::string log;
     degk_ctx tmp;
-    int rc = compile_cubin(&tmp, d, cubin, log);
+    int slots = default_slots(d);
+    int rc = compile_cubin(&tmp, d, slots, cubin, log);
+    if (rc == DEGK_ERR_NVRTC && slots == 2) rc = compile_cubin(&tmp, d, 1, cubin, log);
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     if (msg && msg_cap > 0) {
         const std::string& m = rc == DEGK_OK ? log : tmp.err;
@@ -279,7 +321,9 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     auto t0 = std::chrono::steady_clock::now();
     std::vector<char> cubin;
     std::string log;
-    int rc = compile_cubin(ctx, d, cubin, log);
+    int slots = default_slots(d);
+    int rc = compile_cubin(ctx, d, slots, cubin, log);
+    if (rc == DEGK_ERR_NVRTC && slots == 2) { slots = 1; rc = compile_cubin(ctx, d, slots, cubin, log); }
     if (rc != DEGK_OK) return rc;
     std::call_once(g_drv_once, load_driver);
     if (!g_drv.ok) { degk_set_error(ctx, "CUDA driver API unavailable: %s", g_drv.load_error.c_str()); return DEGK_ERR_CUDA; }
@@ -292,6 +336,9 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     if (!is_sde) DRV(ctx, g_drv.ModuleGetFunction(&f1, mod, "degk_jit_adaptive"));
     prog->jit_fn[0] = f0;
     prog->jit_fn[1] = f1;
+    CUfunction f2 = nullptr;
+    if (!is_sde) DRV(ctx, g_drv.ModuleGetFunction(&f2, mod, "degk_jit_adaptive2"));
+    prog->jit_fn[2] = f2;
     prog->info.is_jit = 1;
     if (d->rhs_src) {
         const int noise = is_sde ? d->noise_kind : 0;
@@ -318,17 +365,28 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     }
     DRV(ctx, g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, f1 ? f1 : f0, DEGK_BLOCK, 0));
     prog->info.max_blocks_per_sm = v;
+    if (f2) {
+        prog->w2 = slots;
+        prog->qcap2 = 32 + 32 * slots;
+        prog->rec_bytes2 = save_rec_bytes(d->dtype, prog->info.n_state);
+        DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, f2)); prog->info.regs_adaptive2 = v;
+        DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f2)); prog->info.local_bytes_adaptive2 = v;
+        prog->info.slots_per_thread2 = slots;
+        const size_t smem = (size_t)(DEGK_BLOCK2 / 32) * prog->qcap2 * prog->rec_bytes2 + 1024 * (d->dtype == DEGK_F64 ? 8 : 4);
+        DRV(ctx, g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, f2, DEGK_BLOCK2, smem));
+        prog->info.max_blocks_per_sm2 = v;
+    }
     prog->info.jit_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return DEGK_OK;
 }
 
-int degk_jit_launch(degk_program* prog, int which, unsigned grid, unsigned block,
+int degk_jit_launch(degk_program* prog, int which, unsigned grid, unsigned block, unsigned smem,
                     const degk::KArgs* args, cudaStream_t stream) {
     degk_ctx* ctx = prog->ctx;
     CUfunction f = (CUfunction)prog->jit_fn[which];
     if (!f) { degk_set_error(ctx, "program has no %s kernel", which ? "adaptive" : "fixed-dt"); return DEGK_ERR_UNSUPPORTED; }
     void* params[1] = {(void*)args};
-    DRV(ctx, g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, (CUstream)stream, params, nullptr));
+    DRV(ctx, g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, smem, (CUstream)stream, params, nullptr));
     return DEGK_OK;
 }
 

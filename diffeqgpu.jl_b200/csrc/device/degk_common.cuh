@@ -90,6 +90,19 @@ DEGK_DEV float pow_(float x, float y) {
 }
 DEGK_DEV double pow_(double x, double y) { return pow(x, y); }
 
+// MUFU log2 / exp2 for the fast-mode controller (log-domain PI controller)
+DEGK_DEV float log2_(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DEGK_DEV float exp2_(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DEGK_DEV double log2_(double x) { return log2(x); }
+DEGK_DEV double exp2_(double x) { return exp2(x); }
+
+DEGK_DEV float rcp_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DEGK_DEV double rcp_(double x) { return 1.0 / x; }
+DEGK_DEV float fmax_(float a, float b) { return fmaxf(a, b); }
+DEGK_DEV float fmin_(float a, float b) { return fminf(a, b); }
+DEGK_DEV double fmax_(double a, double b) { return fmax(a, b); }
+DEGK_DEV double fmin_(double a, double b) { return fmin(a, b); }
+
 // division used only for step-size control quantities (error scaling, q factors)
 DEGK_DEV float ctl_div(float a, float b) {
 #if DEGK_STRICT
@@ -146,6 +159,10 @@ struct Ctl {
 DEGK_DEV u32 lane_id() { u32 r; asm volatile("mov.u32 %0, %%laneid;" : "=r"(r)); return r; }
 
 template <class T> DEGK_DEV bool finite_(T x) { return (x - x) == (T)0; }
+
+// per-slot select used by the packed kernel (W = 1: plain scalar select)
+// m: bit s set => take `a` for slot s
+template <class V> DEGK_DEV V blendm(unsigned m, V a, V b) { return (m & 1u) ? a : b; }
 
 // load u0 / p / tspan of one trajectory (AoS inputs like the reference's probs[i])
 template <class T, class Model>

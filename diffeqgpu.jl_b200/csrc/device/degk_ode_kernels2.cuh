@@ -1,0 +1,390 @@
+// degk_ode_kernels2.cuh -- second-generation adaptive ensemble kernel.
+//
+// Replaces reference kernels.jl:74-152 (ode_asolve_kernel) like degk_ode_kernels.cuh does, with
+// changes that came out of the ncu profiles of the first kernel (profiles/):
+//
+//  (1) DEFERRED, BATCHED SAVES.  In the first kernel 25 % of all issued warp-instructions were
+//      the saveat block (dense-output polynomials + stores) executed with ~2 of 32 lanes active:
+//      with 32 independent adaptive trajectories per warp some lane crosses a save point in
+//      83 % of the iterations.  Here a lane that crosses a save point only appends a small
+//      record {trajectory, row, tprev, h, tnew, uprev} to a per-warp queue in shared memory.
+//      When 32 records are queued the whole warp processes them together, one record per lane:
+//      it re-evaluates the stages of that step (same inputs, same instruction sequence => same
+//      bits), interpolates and stores.  Re-computing a step costs less than 1 % of a trajectory
+//      (11 saves vs ~170 steps) and runs at full SIMT efficiency.
+//
+//  (2) PACKED PAIRS (W = 2, Float32 fast mode).  Each thread advances two trajectories held in
+//      the halves of 64-bit register pairs; stages, RHS and error estimate are FFMA2/FMUL2/FADD2
+//      (see degk_pack.cuh).  The kernel is issue-bound, so halving the instructions per
+//      trajectory nearly doubles the throughput of the arithmetic core.
+//
+//  (3) BRANCH-FREE STEP-SIZE CONTROL (fast mode).  The PI controller is evaluated in the log2
+//      domain: q = EEst^b1 / qold^b2 = 2^(b1*lE - b2*lq), so one MUFU.LG2 and one MUFU.EX2 replace
+//      the square root, two powers and three divisions; accept and reject values are both
+//      computed and selected, flags are bit masks, and only the rare events (save-point
+//      crossing, retirement, refill) branch.
+//
+// W = 1 gives the same kernel for Float64 and for the strict (bit-parity) fp mode.
+#pragma once
+#include "degk_common.cuh"
+#include "degk_pack.cuh"
+
+namespace degk {
+
+// queue record of one deferred save (lives in shared memory)
+template <class T, int N>
+struct __align__(16) SaveRec {
+    i64 traj;
+    int cur;            // 1-based index of the first saveat entry to write
+    T tprev, h, tnew;
+    T u[N];             // state at the beginning of the step
+};
+
+template <class T, int N, int W>
+__host__ __device__ constexpr int asolve2_qcap() { return 32 + 32 * W; }
+
+// copy a record through 16-byte words so that the compiler emits vector shared-memory accesses
+template <class R>
+DEGK_DEV void rec_copy(R* dst, const R* src) {
+    static_assert(sizeof(R) % 16 == 0, "SaveRec must be a multiple of 16 bytes");
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    DEGK_UNROLL for (int i = 0; i < (int)(sizeof(R) / 16); ++i) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// One warp processes up to 32 queued save records, one per lane (scalar method).
+template <class T, class Model, class MethodS>
+DEGK_DEV void process_saves(const KArgs& a, const SaveRec<T, Model::N>* q, int first, int count,
+                            const T* sv) {
+    constexpr int N = Model::N;
+    const int lane = (int)lane_id();
+    if (lane < count) {
+        SaveRec<T, N> r;
+        rec_copy(&r, q + first + lane);
+        T uprev[N], unew[N], err[N];
+        T p[Model::NP > 0 ? Model::NP : 1];
+        DEGK_UNROLL for (int c = 0; c < N; ++c) uprev[c] = r.u[c];
+        if (Model::NP > 0) {
+            const T* pp = (const T*)a.p + r.traj * a.p_stride;
+            DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) p[c] = pp[c];
+        }
+        const T tprev = r.tprev, h = r.h, tnew = r.tnew;
+        typename MethodS::Keep K;
+        MethodS::init(K, uprev, p, tprev);                  // FSAL k1 = f(uprev, p, tprev)
+        MethodS::template attempt<false>(K, uprev, p, tprev, h, unew, err);
+        MethodS::on_accept(K);
+        int cur = r.cur;
+        while (cur <= a.n_saveat && sv[cur - 1] <= tnew) {  // integrator_utils.jl:34-47
+            const T savet = sv[cur - 1];
+            const T theta = (savet - tprev) / h;
+            T v[N];
+            MethodS::interp(K, theta, h, uprev, unew, p, tprev, v);
+            store_u<T, N>(a, r.traj, cur - 1, v);
+            store_t<T>(a, r.traj, cur - 1, savet);
+            ++cur;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <class T, class Model, template <class, class> class MethodT, int W>
+DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
+    typedef PackOf<T, W> PO;
+    typedef typename PO::type V;
+    typedef MethodT<V, Model> MethodV;       // stepping (packed when W == 2)
+    typedef MethodT<T, Model> MethodS;       // scalar: deferred saves, final interpolation
+    typedef Ctl<T, MethodS::ORDER> C;
+    constexpr int N = Model::N;
+    constexpr int NPA = Model::NP > 0 ? Model::NP : 1;
+    constexpr int QCAP = asolve2_qcap<T, N, W>();
+    typedef SaveRec<T, N> Rec;
+
+    const T abstol = (T)a.abstol, reltol = (T)a.reltol;
+    const bool has_saveat = a.saveat != nullptr;
+    const int nsv = has_saveat ? a.n_saveat : 0;
+    const u32 lane = lane_id();
+    const u32 lt_mask = (1u << lane) - 1u;
+    const int warp_in_block = (int)(threadIdx.x >> 5);
+    const int nwarps = (int)(blockDim.x >> 5);
+    const u32 max_it = a.max_iters > 0x7fffffffLL ? 0x7fffffffu : (u32)a.max_iters;
+
+    // shared memory: [per-warp save queues][saveat copy]
+    Rec* queue = (Rec*)smem_raw + (size_t)warp_in_block * QCAP;
+    T* sv_s = (T*)(smem_raw + (size_t)nwarps * QCAP * sizeof(Rec));
+    const T* sv = (const T*)a.saveat;
+    if (has_saveat && a.n_saveat <= 1024) {
+        for (int i = (int)threadIdx.x; i < a.n_saveat; i += (int)blockDim.x) sv_s[i] = sv[i];
+        __syncthreads();
+        sv = sv_s;
+    }
+    int qcount = 0;                          // warp-uniform
+
+    // per-thread state: W trajectories ("slots"); flags are bit masks over the slots
+    V u[N], unew[N], err[N], p[NPA];
+    typename MethodV::Keep K;
+    T t[W], h[W], tf[W], t0[W], next_save[W], lq[W];   // lq: qold (strict) or log2(qold) (fast)
+    int cur[W];
+    i64 traj[W];
+    u32 nacc[W], nrej[W];
+    u32 havem = 0;
+    DEGK_UNROLL for (int s = 0; s < W; ++s) {
+        traj[s] = -1; cur[s] = 0; nacc[s] = 0; nrej[s] = 0;
+        t[s] = (T)0; h[s] = (T)1; tf[s] = (T)0; t0[s] = (T)0; next_save[s] = (T)0; lq[s] = (T)0;
+    }
+    DEGK_UNROLL for (int c = 0; c < N; ++c) { u[c] = V((T)0); unew[c] = V((T)0); err[c] = V((T)0); }
+    DEGK_UNROLL for (int c = 0; c < NPA; ++c) p[c] = V((T)0);
+    DEGK_UNROLL for (int j = 0; j < (int)(sizeof(K) / sizeof(V)); ++j) ((V*)&K)[j] = V((T)0);
+    u32 tot_acc = 0, tot_rej = 0, tot_fail = 0;
+
+    const bool queue_sched = (a.schedule == SCHED_QUEUE);
+    bool exhausted = false;                  // warp-uniform
+    bool static_done = false;
+    const i64 warp_global = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr u32 ALLM = (1u << W) - 1u;
+
+    for (;;) {
+        // ---------------- (re)fill idle slots ----------------
+        if (__any_sync(0xffffffffu, havem != ALLM)) {
+            u32 freshm = 0;
+            DEGK_UNROLL for (int s = 0; s < W; ++s) {
+                const u32 need = __ballot_sync(0xffffffffu, !(havem & (1u << s)));
+                if (need == 0) continue;
+                i64 claim = a.n_traj;
+                if (!exhausted) {
+                    if (queue_sched) {
+                        const int cnt = __popc(need);
+                        const int leader = __ffs(need) - 1;
+                        i64 base = 0;
+                        if ((int)lane == leader) base = (i64)atomicAdd(a.work_counter, (u64)cnt);
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        claim = base + __popc(need & lt_mask);
+                        if (base + cnt >= a.n_traj) exhausted = true;
+                    } else if (!static_done) {
+                        claim = (warp_global * W + s) * 32 + lane;
+                    }
+                }
+                if (!(havem & (1u << s)) && claim < a.n_traj) {
+                    traj[s] = claim;
+                    T us_[N], ps_[NPA], t0_, tf_;
+                    load_problem<T, Model>(a, claim, us_, ps_, t0_, tf_);
+                    DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = PO::set(u[c], s, us_[c]);
+                    DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) p[c] = PO::set(p[c], s, ps_[c]);
+                    t[s] = t0_; t0[s] = t0_; tf[s] = tf_;
+                    h[s] = (T)a.dt;
+#if DEGK_STRICT
+                    lq[s] = C::qoldinit();
+#else
+                    lq[s] = (T)-13.287712379549449;          // log2(qoldinit = 1e-4)
+#endif
+                    nacc[s] = 0; nrej[s] = 0;
+                    cur[s] = 0;                               // kernels.jl:116-126
+                    if (has_saveat) {
+                        cur[s] = 1;
+                        if (t0_ == sv[0]) {
+                            cur[s] = 2;
+                            store_u<T, N>(a, claim, 0, us_);
+                            store_t<T>(a, claim, 0, t0_);
+                        }
+                        next_save[s] = (cur[s] <= nsv) ? sv[cur[s] - 1] : (T)0;
+                    } else {
+                        store_t<T>(a, claim, 0, t0_);
+                        store_u<T, N>(a, claim, 0, us_);
+                    }
+                    if (t0_ < tf_) {
+                        havem |= (1u << s);
+                        freshm |= (1u << s);
+                    } else {                                  // empty time span
+                        if (!has_saveat && !a.save_everystep) { store_u<T, N>(a, claim, 1, us_); store_t<T>(a, claim, 1, t0_); }
+                        if (a.retcode) a.retcode[claim] = RC_SUCCESS;
+                        if (a.naccept) a.naccept[claim] = 0;
+                        if (a.nreject) a.nreject[claim] = 0;
+                    }
+                }
+            }
+            if (!queue_sched) { static_done = true; exhausted = true; }
+            if (__all_sync(0xffffffffu, havem == 0)) {
+                if (exhausted) break;
+                continue;
+            }
+            if (__any_sync(0xffffffffu, freshm != 0)) {
+                T tt0[W];
+                DEGK_UNROLL for (int s = 0; s < W; ++s) tt0[s] = t[s];
+                MethodV::init_sel(K, u, p, PO::make(tt0), freshm);
+            }
+        }
+
+        // ---------------- one attempt for every slot ----------------
+        T tt[W], hh[W];
+        DEGK_UNROLL for (int s = 0; s < W; ++s) { tt[s] = t[s]; hh[s] = h[s]; }
+        const bool solved = MethodV::template attempt<true>(K, u, p, PO::make(tt), PO::make(hh), unew, err);
+
+        // ---------------- step-size control, per slot ----------------
+        u32 accm = 0, pushm = 0, retm = 0, badm = 0;     // accepted / save crossing / retire / failure
+        T tnew_[W];
+        DEGK_UNROLL for (int s = 0; s < W; ++s) {
+            // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol); ODE_DEFAULT_NORM
+            T accn = (T)0;
+            DEGK_UNROLL for (int c = 0; c < N; ++c) {
+                const T uo = PO::get(u[c], s), un = PO::get(unew[c], s), e = PO::get(err[c], s);
+#if DEGK_STRICT
+                const T sc = abstol + jl_max(abs_(uo), abs_(un)) * reltol;
+                const T v = e / sc;
+#else
+                const T sc = fma_(fmax_(abs_(uo), abs_(un)), reltol, abstol);
+                const T v = e * rcp_(sc);
+#endif
+                const T sq = v * v;
+                accn = (c == 0) ? sq : accn + sq;
+            }
+            const T rem = tf[s] - t[s] - h[s];                  // tf - t - dt
+            const T tn = (rem < MethodS::land()) ? tf[s] : t[s] + h[s];
+            T h_next, lq_next;
+            bool reject;
+#if DEGK_STRICT
+            const T EEst = sqrt_(mean_<T, N>(accn));
+            T q, q11 = (T)0;
+            if (EEst == (T)0) {
+                q = (T)1 / C::qmax();
+            } else {
+                q11 = pow_(EEst, C::beta1());
+                q = q11 / pow_(lq[s], C::beta2());
+            }
+            reject = EEst > (T)1;
+            if (reject) {
+                h_next = h[s] / jl_min((T)1 / C::qmin(), q11 / C::gamma());
+                lq_next = lq[s];
+            } else {
+                q = jl_max((T)1 / C::qmax(), jl_min((T)1 / C::qmin(), q / C::gamma()));
+                lq_next = jl_max(EEst, C::qoldinit());
+                h_next = jl_min(abs_(h[s] / q), abs_(rem));
+            }
+#else
+            const T m = mean_<T, N>(accn);                      // EEst^2
+            const T lE = (T)0.5 * log2_(m);                     // log2(EEst); -inf when EEst == 0
+            reject = m > (T)1;
+            // accept: q/gamma = 2^(b1*lE - b2*lq - log2(gamma)) clamped to [1/qmax, 1/qmin]
+            T e2 = fma_(C::beta1(), lE, fma_(-C::beta2(), lq[s], (T)0.15200309344504995));
+            e2 = fmax_((T)-3.321928094887362, fmin_((T)2.321928094887362, e2));
+            const T h_acc = fmin_(abs_(h[s] * exp2_(-e2)), abs_(rem));
+            // reject: dt / min(1/qmin, q11/gamma) = dt * max(qmin, gamma * 2^(-b1*lE))
+            const T h_rej = h[s] * fmax_(C::qmin(), C::gamma() * exp2_(-C::beta1() * lE));
+            h_next = reject ? h_rej : h_acc;
+            lq_next = reject ? lq[s] : fmax_(lE, (T)-13.287712379549449);
+#endif
+            const bool live = (havem >> s) & 1u;
+            const bool too_small = h[s] < MethodS::dtmin();     // `dt < dtmin && error(...)`
+            const bool ok = live && solved && !too_small;
+            const bool accept = ok && !reject;
+            const bool finished = accept && !(tn < tf[s]);
+            // non-finite time or step size: the reference would spin on NaNs; report Unstable
+            const bool bad_num = accept && !finished && !(abs_(tn + h_next) < (T)(sizeof(T) == 4 ? 3.0e38 : 1.0e300));
+            const bool too_many = ok && (nacc[s] + nrej[s] + 1u >= max_it);
+            const bool fail = live && (!solved || too_small || bad_num || too_many);
+            tnew_[s] = tn;
+            if (accept) ++nacc[s];
+            if (ok && reject) ++nrej[s];
+            if (accept && has_saveat && cur[s] <= nsv && next_save[s] <= tn) pushm |= (1u << s);
+            if (accept) accm |= (1u << s);
+            if (finished || fail) retm |= (1u << s);
+            if (fail) badm |= (1u << s);
+            if (ok) {
+                h[s] = h_next;
+                lq[s] = lq_next;
+                if (accept) t[s] = tn;
+            }
+        }
+
+        // ---------------- queue the deferred saves ----------------
+        if (__any_sync(0xffffffffu, pushm != 0)) {
+            DEGK_UNROLL for (int s = 0; s < W; ++s) {
+                const bool ps = (pushm >> s) & 1u;
+                const u32 pm = __ballot_sync(0xffffffffu, ps);
+                if (ps) {
+                    Rec r;
+                    r.traj = traj[s];
+                    r.cur = cur[s];
+                    r.tprev = tt[s];
+                    r.h = hh[s];
+                    r.tnew = tnew_[s];
+                    DEGK_UNROLL for (int c = 0; c < N; ++c) r.u[c] = PO::get(u[c], s);
+                    rec_copy(queue + qcount + __popc(pm & lt_mask), &r);
+                    do {                                        // skip every save point inside this step
+                        ++cur[s];
+                        next_save[s] = (cur[s] <= nsv) ? sv[cur[s] - 1] : (T)0;
+                    } while (cur[s] <= nsv && next_save[s] <= tnew_[s]);
+                }
+                qcount += __popc(pm);
+            }
+            __syncwarp();
+            while (qcount >= 32) {
+                process_saves<T, Model, MethodS>(a, queue, qcount - 32, 32, sv);
+                qcount -= 32;
+                __syncwarp();
+            }
+        }
+
+        // ---------------- retire finished / failed trajectories ----------------
+        if (__any_sync(0xffffffffu, retm != 0)) {
+            DEGK_UNROLL for (int s = 0; s < W; ++s) {
+                if ((retm >> s) & 1u) {
+                    int rc = RC_SUCCESS;
+                    if ((badm >> s) & 1u) {
+                        if (!solved) rc = RC_SINGULAR;
+                        else if (hh[s] < MethodS::dtmin()) rc = RC_DT_LESS_THAN_MIN;
+                        else if (nacc[s] + nrej[s] >= max_it) rc = RC_MAXITERS;
+                        else rc = RC_UNSTABLE;
+                    } else {
+                        T uf[N], up[N];
+                        DEGK_UNROLL for (int c = 0; c < N; ++c) { uf[c] = PO::get(unew[c], s); up[c] = PO::get(u[c], s); }
+                        if (tnew_[s] > tf[s] && !has_saveat) {   // kernels.jl:133-137 (first-step overshoot)
+                            T ps_[NPA];
+                            DEGK_UNROLL for (int c = 0; c < NPA; ++c) ps_[c] = PO::get(p[c], s);
+                            typename MethodS::Keep Ks;
+                            T un2[N], e2[N], v[N];
+                            MethodS::init(Ks, up, ps_, tt[s]);
+                            MethodS::template attempt<false>(Ks, up, ps_, tt[s], hh[s], un2, e2);
+                            MethodS::on_accept(Ks);
+                            MethodS::interp(Ks, (tf[s] - tt[s]) / hh[s], hh[s], up, un2, ps_, tt[s], v);
+                            store_u<T, N>(a, traj[s], a.n_rows - 1, v);
+                            store_t<T>(a, traj[s], a.n_rows - 1, tf[s]);
+                        }
+                        if (!has_saveat && !a.save_everystep) {  // kernels.jl:139-142
+                            store_u<T, N>(a, traj[s], 1, uf);
+                            store_t<T>(a, traj[s], 1, tnew_[s]);
+                        }
+                        bool fin = true;
+                        DEGK_UNROLL for (int c = 0; c < N; ++c) fin = fin && finite_(uf[c]);
+                        if (!fin) rc = RC_UNSTABLE;
+                    }
+                    i64 first_unwritten;
+                    if (has_saveat) first_unwritten = cur[s] - 1;
+                    else first_unwritten = (rc == RC_SUCCESS && !a.save_everystep) ? 2 : 1;
+                    fill_unwritten_ts<T>(a, traj[s], first_unwritten, t0[s]);
+                    if (a.retcode) a.retcode[traj[s]] = rc;
+                    if (a.naccept) a.naccept[traj[s]] = (int)nacc[s];
+                    if (a.nreject) a.nreject[traj[s]] = (int)nrej[s];
+                    tot_acc += nacc[s]; tot_rej += nrej[s];
+                    if (rc != RC_SUCCESS) ++tot_fail;
+                    havem &= ~(1u << s);
+                    accm &= ~(1u << s);
+                }
+            }
+        }
+
+        // ---------------- commit accepted steps ----------------
+        DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = blendm(accm, unew[c], u[c]);
+        MethodV::accepted_sel(K, accm);
+    }
+    // flush the remaining deferred saves
+    __syncwarp();
+    while (qcount > 0) {
+        const int n = qcount < 32 ? qcount : 32;
+        process_saves<T, Model, MethodS>(a, queue, qcount - n, n, sv);
+        qcount -= n;
+        __syncwarp();
+    }
+    add_totals<T>(a, tot_acc, tot_rej, tot_fail);
+}
+
+}  // namespace degk

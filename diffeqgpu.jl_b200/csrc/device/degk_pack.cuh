@@ -24,8 +24,8 @@ struct Pk2 {
     DEGK_DEV explicit Pk2(float a) { asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(a)); }
     DEGK_DEV explicit Pk2(double a) { const float f = (float)a; asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(f)); }
     DEGK_DEV explicit Pk2(int a) { const float f = (float)a; asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(f)); }
-    DEGK_DEV float lo() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-    DEGK_DEV float hi() const { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+    DEGK_DEV float lo() const { float a; asm("mov.b64 {%0, _}, %1;" : "=f"(a) : "l"(v)); return a; }
+    DEGK_DEV float hi() const { float b; asm("mov.b64 {_, %0}, %1;" : "=f"(b) : "l"(v)); return b; }
     DEGK_DEV float get(int s) const { return s ? hi() : lo(); }
 };
 
@@ -38,5 +38,22 @@ DEGK_DEV Pk2 fma_(Pk2 a, Pk2 b, Pk2 c) {
 }
 // per-half select: s0 ? a.lo : b.lo , s1 ? a.hi : b.hi
 DEGK_DEV Pk2 select2(bool s0, bool s1, Pk2 a, Pk2 b) { return Pk2(s0 ? a.lo() : b.lo(), s1 ? a.hi() : b.hi()); }
+
+DEGK_DEV Pk2 blendm(unsigned m, Pk2 a, Pk2 b) { return select2((m & 1u) != 0, (m & 2u) != 0, a, b); }
+
+// PackOf<T, W>: the value type that carries W trajectories of element type T
+template <class T, int W> struct PackOf;
+template <class T> struct PackOf<T, 1> {
+    typedef T type;
+    static DEGK_DEV T get(T v, int) { return v; }
+    static DEGK_DEV T make(const T (&s)[1]) { return s[0]; }
+    static DEGK_DEV T set(T, int, T x) { return x; }
+};
+template <> struct PackOf<float, 2> {
+    typedef Pk2 type;
+    static DEGK_DEV float get(Pk2 v, int s) { return s ? v.hi() : v.lo(); }
+    static DEGK_DEV Pk2 make(const float (&s)[2]) { return Pk2(s[0], s[1]); }
+    static DEGK_DEV Pk2 set(Pk2 v, int s, float x) { return s == 0 ? Pk2(x, v.hi()) : Pk2(v.lo(), x); }
+};
 
 }  // namespace degk

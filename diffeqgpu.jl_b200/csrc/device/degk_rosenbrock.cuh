@@ -137,6 +137,8 @@ struct Rosenbrock23 {
     static DEGK_DEV void init(Keep&, const T (&)[N], const T*, T) {}
     static DEGK_DEV void accepted(Keep&) {}
     static DEGK_DEV void on_accept(Keep&) {}
+    static DEGK_DEV void init_sel(Keep&, const T (&)[N], const T*, T, unsigned) {}
+    static DEGK_DEV void accepted_sel(Keep&, unsigned) {}
 
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
@@ -204,6 +206,8 @@ struct Rodas {
     static DEGK_DEV T land()  { return (T)1.0e-14f; }
     static DEGK_DEV void init(Keep&, const T (&)[N], const T*, T) {}
     static DEGK_DEV void accepted(Keep&) {}
+    static DEGK_DEV void init_sel(Keep&, const T (&)[N], const T*, T, unsigned) {}
+    static DEGK_DEV void accepted_sel(Keep&, unsigned) {}
 
 #define R4C(x) ((T)rodas4c::x)
 #define R5C(x) ((T)rodas5pc::x)

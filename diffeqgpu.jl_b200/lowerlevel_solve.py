@@ -105,7 +105,7 @@ def _ptr(t):
 
 
 def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_everystep, n_rows,
-            fp_mode, schedule, layout, stats, stream, traj_offset=0, reduce=None):
+            fp_mode, schedule, layout, stats, stream, traj_offset=0, reduce=None, engine="auto"):
     if not isinstance(probs, ProblemBatch):
         probs = adapt("cuda", probs)
     dev = probs.device
@@ -154,6 +154,7 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
         a.seed = int(getattr(probs, "seed", 0)) & 0xFFFFFFFFFFFFFFFF
         a.reduce = None if reduce is None else reduce.data_ptr()
         a.max_iters = 0
+        a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
         s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
         prog.solve(a, s)
         # keep inputs alive until the stream has consumed them
@@ -202,7 +203,7 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
 def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save_everystep=False,
                       abstol=np.float32(1e-6), reltol=np.float32(1e-3), debug=False, callback=None,
                       tstops=None, fp_mode="strict", schedule="auto", layout="ref", stats=False,
-                      stream=None, **kwargs):
+                      stream=None, engine="auto", **kwargs):
     """Adaptive batched solve (defaults as lowerlevel_solve.jl:253-260)."""
     if isinstance(prob, SDEProblem):
         raise RuntimeError("Adaptive time-stepping is not supported yet with GPUEM.")   # :348-356
@@ -224,4 +225,4 @@ def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save
         n_rows = len(saveat_c)
     return _launch(probs, prob, alg, dt=dt, adaptive=True, abstol=abstol, reltol=reltol,
                    saveat=saveat_c, save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
-                   schedule=schedule, layout=layout, stats=stats, stream=stream)
+                   schedule=schedule, layout=layout, stats=stats, stream=stream, engine=engine)

@@ -161,7 +161,7 @@ def _with_seed(prob, seed):
 def solve_host(prob, alg, *, u0=None, p=None, tspan=None, n_traj=None, dt, adaptive=False,
                abstol=1e-6, reltol=1e-3, saveat=None, save_everystep=True, fp_mode="strict",
                schedule="auto", layout="ref", chunk_traj=0, out=None, stats=False, device=None,
-               seed=0, traj_offset=0, reduce=False):
+               seed=0, traj_offset=0, reduce=False, engine="auto"):
     """End-to-end solve with HOST (numpy / pinned torch) buffers through `degk_solve_host`:
     the `batch_solve_up_kernel` equivalent (src/solve.jl:382-419) with the H2D upload of the
     problems, the solve and the D2H download of (ts, us) pipelined in chunks over three streams.
@@ -227,6 +227,7 @@ def solve_host(prob, alg, *, u0=None, p=None, tspan=None, n_traj=None, dt, adapt
     a.out_layout = _lib.LAYOUT_REF if layout == "ref" else _lib.LAYOUT_SOA
     a.schedule = SCHEDULES[schedule]
     a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
     st = {}
     if stats:
         st = dict(retcode=np.zeros(N, np.int32), naccept=np.zeros(N, np.int32),

@@ -86,6 +86,11 @@ typedef enum {
     DEGK_RC_SINGULAR = 5          /* reference: SingularException, linalg/lu.jl:41-44 */
 } degk_retcode;
 
+/* DEGK_ENGINE_AUTO picks the second-generation adaptive kernel (batched deferred saves, two
+ * trajectories per thread in FFMA2 register pairs for Float32 fast mode) when the program has
+ * one; DEGK_ENGINE_V1 forces the first-generation kernel (kept for A/B measurements). */
+typedef enum { DEGK_ENGINE_AUTO = 0, DEGK_ENGINE_V1 = 1 } degk_engine;
+
 typedef enum { DEGK_NOISE_NONE = 0, DEGK_NOISE_DIAGONAL = 1, DEGK_NOISE_GENERAL = 2 } degk_noise;
 
 /* Model description.  Either `builtin` names a model compiled into the library
@@ -115,6 +120,8 @@ typedef struct {
     int32_t regs_fixed, regs_adaptive;     /* registers per thread of the two kernels (0 = n/a) */
     int32_t local_bytes_fixed, local_bytes_adaptive; /* local-memory (spill) bytes per thread */
     int32_t max_blocks_per_sm;  /* occupancy of the adaptive (or only) kernel at 256 threads */
+    /* second-generation adaptive kernel (deferred saves; packed pairs when slots_per_thread2 == 2) */
+    int32_t regs_adaptive2, local_bytes_adaptive2, slots_per_thread2, max_blocks_per_sm2;
     double jit_seconds;         /* NVRTC compile + module load time */
 } degk_program_info;
 
@@ -147,6 +154,8 @@ typedef struct {
                               trajectories of this call (SDE kernels; needs tspan_stride == 0) */
     uint64_t* totals;      /* optional inout [4]: += accepted, rejected, failed, 0 */
     int64_t max_iters;     /* 0 => 1e9 */
+    int32_t engine;        /* degk_engine: which adaptive kernel generation to run */
+    int32_t reserved;
 } degk_solve_args;
 
 DEGK_API int degk_version(void);

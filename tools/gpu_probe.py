@@ -21,12 +21,12 @@ def lorenz_batch(N, dtype=np.float32, seed=0, dev="cuda:0"):
     return prob, dg.ProblemBatch.from_arrays(prob, p=p, device=dev)
 
 
-def time_asolve(N, fp_mode, schedule, alg=None, reps=3, dtype=np.float32, tol=1e-6):
+def time_asolve(N, fp_mode, schedule, alg=None, reps=3, dtype=np.float32, tol=1e-6, engine="auto"):
     alg = alg or dg.GPUTsit5()
     prob, probs = lorenz_batch(N, dtype)
     saveat = np.arange(0, 11, dtype=dtype)
     kw = dict(dt=dtype(0.1), saveat=saveat, abstol=dtype(tol), reltol=dtype(tol), fp_mode=fp_mode,
-              schedule=schedule, stats=True)
+              schedule=schedule, stats=True, engine=engine)
     ts, us, st = dg.vectorized_asolve(probs, prob, alg, **kw)
     torch.cuda.synchronize()
     best = 1e9
@@ -42,17 +42,19 @@ def time_asolve(N, fp_mode, schedule, alg=None, reps=3, dtype=np.float32, tol=1e
     info = dg.get_program(prob, alg, fp_mode).info
     return dict(N=N, fp=fp_mode, sched=schedule, alg=type(alg).__name__, ms=round(best, 3),
                 steps=steps, acc=int(tot[0]), rej=int(tot[1]), fail=int(tot[2]),
-                gsteps_per_s=round(steps / best / 1e6, 3), regs=info.regs_adaptive,
-                occ=info.max_blocks_per_sm)
+                gsteps_per_s=round(steps / best / 1e6, 3), engine=engine,
+                regs=(info.regs_adaptive, info.regs_adaptive2), occ=(info.max_blocks_per_sm, info.max_blocks_per_sm2),
+                slots=info.slots_per_thread2)
 
 
 if __name__ == "__main__":
     out = []
     N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 22
-    for fp in ("strict", "fast"):
-        for sched in ("static", "queue"):
-            r = time_asolve(N, fp, sched)
-            print(json.dumps(r), flush=True)
-            out.append(r)
+    for eng in ("v1", "auto"):
+        for fp in ("strict", "fast"):
+            for sched in ("static", "queue"):
+                r = time_asolve(N, fp, sched, engine=eng)
+                print(json.dumps(r), flush=True)
+                out.append(r)
     Path("gpurun_out").mkdir(exist_ok=True)
     Path("gpurun_out/probe.json").write_text(json.dumps(out, indent=1))
