@@ -63,6 +63,15 @@ void degk_set_error(degk_ctx* ctx, const char* fmt, ...) {
 
 static size_t dtype_size(int dtype) { return dtype == DEGK_F64 ? 8 : 4; }
 
+// dynamic shared memory of the second-generation adaptive kernel (degk_ode_kernels2.cuh):
+// per-warp save queues + per-warp problem pools (32 x (n + np + 2) values) + saveat copy
+size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged) {
+    const size_t es = dtype_size(prog->info.dtype);
+    const size_t nw = DEGK_BLOCK2 / 32;
+    return nw * prog->qcap2 * prog->rec_bytes2 + nw * 32 * (size_t)(prog->info.n_state + prog->info.n_param + 2) * es +
+           (size_t)n_saveat_staged * es;
+}
+
 extern "C" int degk_version(void) { return DEGK_VERSION; }
 
 extern "C" const char* degk_last_error(degk_ctx* ctx) {
@@ -214,7 +223,8 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
                 prog->info.regs_adaptive2 = fa.numRegs;
                 prog->info.local_bytes_adaptive2 = (int)fa.localSizeBytes;
                 prog->info.slots_per_thread2 = prog->w2;
-                const size_t smem = (size_t)(DEGK_BLOCK2 / 32) * prog->qcap2 * prog->rec_bytes2 + 1024 * dtype_size(d->dtype);
+                const size_t smem = degk_smem2_bytes(prog, 1024);
+                if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(prog->fn[2], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prog->fn[2], DEGK_BLOCK2, smem));
                 prog->info.max_blocks_per_sm2 = occ;
             }
@@ -370,7 +380,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     size_t smem = 0;
     if (v2) {
         const int nsv = (a->saveat && a->n_saveat <= 1024) ? a->n_saveat : 0;
-        smem = (size_t)(DEGK_BLOCK2 / 32) * prog->qcap2 * prog->rec_bytes2 + (size_t)nsv * dtype_size(prog->info.dtype);
+        smem = degk_smem2_bytes(prog, nsv);
     }
     long long blocks = (a->n_traj + per_block - 1) / per_block;
     if (sched == DEGK_SCHED_QUEUE) {

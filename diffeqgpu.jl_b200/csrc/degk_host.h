@@ -40,6 +40,7 @@ struct degk_program {
 };
 
 void degk_set_error(degk_ctx* ctx, const char* fmt, ...);
+size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged);
 
 // NVRTC path (degk_jit.cpp)
 int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog);

@@ -79,6 +79,7 @@ struct Driver {
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              unsigned, CUstream, void**, void**);
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction);
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
     CUresult (*GetErrorString)(CUresult, const char**);
     std::string load_error;
@@ -101,6 +102,7 @@ void load_driver() {
     DSYM(ModuleUnload, "cuModuleUnload")
     DSYM(LaunchKernel, "cuLaunchKernel")
     DSYM(FuncGetAttribute, "cuFuncGetAttribute")
+    DSYM(FuncSetAttribute, "cuFuncSetAttribute")
     DSYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
     DSYM(GetErrorString, "cuGetErrorString")
 #undef DSYM
@@ -372,7 +374,8 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
         DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, f2)); prog->info.regs_adaptive2 = v;
         DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f2)); prog->info.local_bytes_adaptive2 = v;
         prog->info.slots_per_thread2 = slots;
-        const size_t smem = (size_t)(DEGK_BLOCK2 / 32) * prog->qcap2 * prog->rec_bytes2 + 1024 * (d->dtype == DEGK_F64 ? 8 : 4);
+        const size_t smem = degk_smem2_bytes(prog, 1024);
+        if (smem > 48 * 1024) DRV(ctx, g_drv.FuncSetAttribute(f2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
         DRV(ctx, g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, f2, DEGK_BLOCK2, smem));
         prog->info.max_blocks_per_sm2 = v;
     }

@@ -108,10 +108,12 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
     const int warp_in_block = (int)(threadIdx.x >> 5);
     const int nwarps = (int)(blockDim.x >> 5);
     const u32 max_it = a.max_iters > 0x7fffffffLL ? 0x7fffffffu : (u32)a.max_iters;
+    const T kInf = (T)__longlong_as_double(0x7ff0000000000000LL);   // +inf: "no further save point"
 
-    // shared memory: [per-warp save queues][saveat copy]
+    // shared memory: [per-warp save queues][per-warp problem pools][saveat copy]
     Rec* queue = (Rec*)smem_raw + (size_t)warp_in_block * QCAP;
-    T* sv_s = (T*)(smem_raw + (size_t)nwarps * QCAP * sizeof(Rec));
+    T* pool = (T*)(smem_raw + (size_t)nwarps * QCAP * sizeof(Rec)) + (size_t)warp_in_block * 32 * (N + Model::NP + 2);
+    T* sv_s = (T*)(smem_raw + (size_t)nwarps * QCAP * sizeof(Rec)) + (size_t)nwarps * 32 * (N + Model::NP + 2);
     const T* sv = (const T*)a.saveat;
     if (has_saveat && a.n_saveat <= 1024) {
         for (int i = (int)threadIdx.x; i < a.n_saveat; i += (int)blockDim.x) sv_s[i] = sv[i];
@@ -123,14 +125,14 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
     // per-thread state: W trajectories ("slots"); flags are bit masks over the slots
     V u[N], unew[N], err[N], p[NPA];
     typename MethodV::Keep K;
-    T t[W], h[W], tf[W], t0[W], next_save[W], lq[W];   // lq: qold (strict) or log2(qold) (fast)
+    T t[W], h[W], tf[W], next_save[W], next_save2[W], lq[W];   // lq: qold (strict) or log2(qold) (fast)
     int cur[W];
     i64 traj[W];
     u32 nacc[W], nrej[W];
     u32 havem = 0;
     DEGK_UNROLL for (int s = 0; s < W; ++s) {
         traj[s] = -1; cur[s] = 0; nacc[s] = 0; nrej[s] = 0;
-        t[s] = (T)0; h[s] = (T)1; tf[s] = (T)0; t0[s] = (T)0; next_save[s] = (T)0; lq[s] = (T)0;
+        t[s] = (T)0; h[s] = (T)1; tf[s] = (T)0; next_save[s] = kInf; next_save2[s] = kInf; lq[s] = (T)0;
     }
     DEGK_UNROLL for (int c = 0; c < N; ++c) { u[c] = V((T)0); unew[c] = V((T)0); err[c] = V((T)0); }
     DEGK_UNROLL for (int c = 0; c < NPA; ++c) p[c] = V((T)0);
@@ -143,68 +145,112 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
     const i64 warp_global = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     constexpr u32 ALLM = (1u << W) - 1u;
 
+    // Claimed-but-not-started trajectories are staged in a per-warp pool in shared memory: one
+    // atomicAdd and one round of coalesced global loads per 32 trajectories, instead of an
+    // atomic + dependent loads (~1000 cycles of exposed latency) every time a lane retires.
+    constexpr int PW = N + Model::NP + 2;    // words per pooled problem: u0, p, t0, tf
+    i64 pool_base = 0;                       // warp-uniform
+    int pool_n = 0, pool_pos = 0;
+
+    // start trajectory `claim` (problem data in us_/ps_/t0_/tf_) in slot s of this lane
+    auto start_slot = [&](int s, i64 claim, const T (&us_)[N], const T (&ps_)[NPA], T t0_, T tf_, u32& freshm) {
+        traj[s] = claim;
+        DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = PO::set(u[c], s, us_[c]);
+        DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) p[c] = PO::set(p[c], s, ps_[c]);
+        t[s] = t0_; tf[s] = tf_;
+        h[s] = (T)a.dt;
+#if DEGK_STRICT
+        lq[s] = C::qoldinit();
+#else
+        lq[s] = (T)-13.287712379549449;          // log2(qoldinit = 1e-4)
+#endif
+        nacc[s] = 0; nrej[s] = 0;
+        cur[s] = 0;                               // kernels.jl:116-126
+        if (has_saveat) {
+            cur[s] = 1;
+            if (t0_ == sv[0]) {
+                cur[s] = 2;
+                store_u<T, N>(a, claim, 0, us_);
+                store_t<T>(a, claim, 0, t0_);
+            }
+            next_save[s] = (cur[s] <= nsv) ? sv[cur[s] - 1] : kInf;
+            next_save2[s] = (cur[s] + 1 <= nsv) ? sv[cur[s]] : kInf;
+        } else {
+            next_save[s] = kInf;
+            next_save2[s] = kInf;
+            store_t<T>(a, claim, 0, t0_);
+            store_u<T, N>(a, claim, 0, us_);
+        }
+        if (t0_ < tf_) {
+            havem |= (1u << s);
+            freshm |= (1u << s);
+        } else {                                  // empty time span
+            if (!has_saveat && !a.save_everystep) { store_u<T, N>(a, claim, 1, us_); store_t<T>(a, claim, 1, t0_); }
+            if (a.retcode) a.retcode[claim] = RC_SUCCESS;
+            if (a.naccept) a.naccept[claim] = 0;
+            if (a.nreject) a.nreject[claim] = 0;
+        }
+    };
+
     for (;;) {
         // ---------------- (re)fill idle slots ----------------
         if (__any_sync(0xffffffffu, havem != ALLM)) {
             u32 freshm = 0;
             DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                const u32 need = __ballot_sync(0xffffffffu, !(havem & (1u << s)));
+                const bool mine = !(havem & (1u << s));
+                const u32 need = __ballot_sync(0xffffffffu, mine);
                 if (need == 0) continue;
-                i64 claim = a.n_traj;
-                if (!exhausted) {
-                    if (queue_sched) {
-                        const int cnt = __popc(need);
-                        const int leader = __ffs(need) - 1;
-                        i64 base = 0;
-                        if ((int)lane == leader) base = (i64)atomicAdd(a.work_counter, (u64)cnt);
-                        base = __shfl_sync(0xffffffffu, base, leader);
-                        claim = base + __popc(need & lt_mask);
-                        if (base + cnt >= a.n_traj) exhausted = true;
-                    } else if (!static_done) {
-                        claim = (warp_global * W + s) * 32 + lane;
-                    }
-                }
-                if (!(havem & (1u << s)) && claim < a.n_traj) {
-                    traj[s] = claim;
-                    T us_[N], ps_[NPA], t0_, tf_;
-                    load_problem<T, Model>(a, claim, us_, ps_, t0_, tf_);
-                    DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = PO::set(u[c], s, us_[c]);
-                    DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) p[c] = PO::set(p[c], s, ps_[c]);
-                    t[s] = t0_; t0[s] = t0_; tf[s] = tf_;
-                    h[s] = (T)a.dt;
-#if DEGK_STRICT
-                    lq[s] = C::qoldinit();
-#else
-                    lq[s] = (T)-13.287712379549449;          // log2(qoldinit = 1e-4)
-#endif
-                    nacc[s] = 0; nrej[s] = 0;
-                    cur[s] = 0;                               // kernels.jl:116-126
-                    if (has_saveat) {
-                        cur[s] = 1;
-                        if (t0_ == sv[0]) {
-                            cur[s] = 2;
-                            store_u<T, N>(a, claim, 0, us_);
-                            store_t<T>(a, claim, 0, t0_);
+                if (queue_sched) {
+                    const int cnt = __popc(need);
+                    const int rank = __popc(need & lt_mask);
+                    int served = 0;
+                    while (served < cnt) {
+                        if (pool_pos == pool_n) {                 // pool empty: claim the next 32
+                            if (exhausted) break;
+                            i64 base = 0;
+                            if (lane == 0) base = (i64)atomicAdd(a.work_counter, (u64)32);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            i64 left = a.n_traj - base;
+                            int n = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+                            if (base + 32 >= a.n_traj) exhausted = true;
+                            if ((int)lane < n) {
+                                T us_[N], ps_[NPA], t0_, tf_;
+                                load_problem<T, Model>(a, base + lane, us_, ps_, t0_, tf_);
+                                T* e = pool + lane * PW;
+                                DEGK_UNROLL for (int c = 0; c < N; ++c) e[c] = us_[c];
+                                DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) e[N + c] = ps_[c];
+                                e[N + Model::NP] = t0_; e[N + Model::NP + 1] = tf_;
+                            }
+                            __syncwarp();
+                            pool_base = base; pool_n = n; pool_pos = 0;
+                            if (n == 0) break;
                         }
-                        next_save[s] = (cur[s] <= nsv) ? sv[cur[s] - 1] : (T)0;
-                    } else {
-                        store_t<T>(a, claim, 0, t0_);
-                        store_u<T, N>(a, claim, 0, us_);
+                        const int avail = pool_n - pool_pos;
+                        const int take = avail < cnt - served ? avail : cnt - served;
+                        if (mine && rank >= served && rank < served + take) {
+                            const int ei = pool_pos + rank - served;
+                            const T* e = pool + ei * PW;
+                            T us_[N], ps_[NPA];
+                            DEGK_UNROLL for (int c = 0; c < N; ++c) us_[c] = e[c];
+                            DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) ps_[c] = e[N + c];
+                            start_slot(s, pool_base + ei, us_, ps_, e[N + Model::NP], e[N + Model::NP + 1], freshm);
+                        }
+                        pool_pos += take;
+                        served += take;
                     }
-                    if (t0_ < tf_) {
-                        havem |= (1u << s);
-                        freshm |= (1u << s);
-                    } else {                                  // empty time span
-                        if (!has_saveat && !a.save_everystep) { store_u<T, N>(a, claim, 1, us_); store_t<T>(a, claim, 1, t0_); }
-                        if (a.retcode) a.retcode[claim] = RC_SUCCESS;
-                        if (a.naccept) a.naccept[claim] = 0;
-                        if (a.nreject) a.nreject[claim] = 0;
+                    __syncwarp();
+                } else if (!static_done) {
+                    const i64 claim = (warp_global * W + s) * 32 + lane;
+                    if (mine && claim < a.n_traj) {
+                        T us_[N], ps_[NPA], t0_, tf_;
+                        load_problem<T, Model>(a, claim, us_, ps_, t0_, tf_);
+                        start_slot(s, claim, us_, ps_, t0_, tf_, freshm);
                     }
                 }
             }
             if (!queue_sched) { static_done = true; exhausted = true; }
             if (__all_sync(0xffffffffu, havem == 0)) {
-                if (exhausted) break;
+                if (exhausted && pool_pos == pool_n) break;
                 continue;
             }
             if (__any_sync(0xffffffffu, freshm != 0)) {
@@ -272,27 +318,26 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
             h_next = reject ? h_rej : h_acc;
             lq_next = reject ? lq[s] : fmax_(lE, (T)-13.287712379549449);
 #endif
-            const bool live = (havem >> s) & 1u;
-            const bool too_small = h[s] < MethodS::dtmin();     // `dt < dtmin && error(...)`
-            const bool ok = live && solved && !too_small;
-            const bool accept = ok && !reject;
-            const bool finished = accept && !(tn < tf[s]);
+            // flags as 0/1 integers combined with bitwise ops: no short-circuit branches
+            const u32 live = (havem >> s) & 1u;
+            const u32 too_small = h[s] < MethodS::dtmin();      // `dt < dtmin && error(...)`
+            const u32 ok = live & (u32)solved & (too_small ^ 1u);
+            const u32 accept = ok & ((u32)reject ^ 1u);
+            const u32 finished = accept & (u32)!(tn < tf[s]);
             // non-finite time or step size: the reference would spin on NaNs; report Unstable
-            const bool bad_num = accept && !finished && !(abs_(tn + h_next) < (T)(sizeof(T) == 4 ? 3.0e38 : 1.0e300));
-            const bool too_many = ok && (nacc[s] + nrej[s] + 1u >= max_it);
-            const bool fail = live && (!solved || too_small || bad_num || too_many);
+            const u32 bad_num = accept & (finished ^ 1u) & (u32)!(abs_(tn + h_next) < (T)(sizeof(T) == 4 ? 3.0e38 : 1.0e300));
+            const u32 too_many = ok & (u32)(nacc[s] + nrej[s] + 1u >= max_it);
+            const u32 fail = live & (((u32)solved ^ 1u) | too_small | bad_num | too_many);
             tnew_[s] = tn;
-            if (accept) ++nacc[s];
-            if (ok && reject) ++nrej[s];
-            if (accept && has_saveat && cur[s] <= nsv && next_save[s] <= tn) pushm |= (1u << s);
-            if (accept) accm |= (1u << s);
-            if (finished || fail) retm |= (1u << s);
-            if (fail) badm |= (1u << s);
-            if (ok) {
-                h[s] = h_next;
-                lq[s] = lq_next;
-                if (accept) t[s] = tn;
-            }
+            nacc[s] += accept;
+            nrej[s] += ok & (u32)reject;
+            pushm |= (accept & (u32)(next_save[s] <= tn)) << s;   // next_save = +inf past the last point
+            accm |= accept << s;
+            retm |= (finished | fail) << s;
+            badm |= fail << s;
+            h[s] = ok ? h_next : h[s];
+            lq[s] = ok ? lq_next : lq[s];
+            t[s] = accept ? tn : t[s];
         }
 
         // ---------------- queue the deferred saves ----------------
@@ -309,10 +354,15 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
                     r.tnew = tnew_[s];
                     DEGK_UNROLL for (int c = 0; c < N; ++c) r.u[c] = PO::get(u[c], s);
                     rec_copy(queue + qcount + __popc(pm & lt_mask), &r);
-                    do {                                        // skip every save point inside this step
+                    // advance to the next save point; its time was prefetched into next_save2 at
+                    // the previous crossing, so the shared-memory load issued here is not waited on
+                    ++cur[s];
+                    next_save[s] = next_save2[s];
+                    while (cur[s] <= nsv && next_save[s] <= tnew_[s]) {   // several save points in one step
                         ++cur[s];
-                        next_save[s] = (cur[s] <= nsv) ? sv[cur[s] - 1] : (T)0;
-                    } while (cur[s] <= nsv && next_save[s] <= tnew_[s]);
+                        next_save[s] = (cur[s] <= nsv) ? sv[cur[s] - 1] : kInf;
+                    }
+                    next_save2[s] = (cur[s] + 1 <= nsv) ? sv[cur[s]] : kInf;
                 }
                 qcount += __popc(pm);
             }
@@ -360,7 +410,7 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
                     i64 first_unwritten;
                     if (has_saveat) first_unwritten = cur[s] - 1;
                     else first_unwritten = (rc == RC_SUCCESS && !a.save_everystep) ? 2 : 1;
-                    fill_unwritten_ts<T>(a, traj[s], first_unwritten, t0[s]);
+                    fill_unwritten_ts<T>(a, traj[s], first_unwritten, ((const T*)a.tspan)[traj[s] * a.tspan_stride]);
                     if (a.retcode) a.retcode[traj[s]] = rc;
                     if (a.naccept) a.naccept[traj[s]] = (int)nacc[s];
                     if (a.nreject) a.nreject[traj[s]] = (int)nrej[s];

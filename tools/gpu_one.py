@@ -12,4 +12,4 @@ fp, sched, N = sys.argv[1], sys.argv[2], int(float(sys.argv[3]))
 alg = getattr(dg, sys.argv[4])() if len(sys.argv) > 4 else dg.GPUTsit5()
 dtype = np.float64 if len(sys.argv) > 5 and sys.argv[5] == "f64" else np.float32
 tol = float(sys.argv[6]) if len(sys.argv) > 6 else 1e-6
-print(time_asolve(N, fp, sched, alg=alg, reps=1, dtype=dtype, tol=tol))
+print(time_asolve(N, fp, sched, alg=alg, reps=4, dtype=dtype, tol=tol))

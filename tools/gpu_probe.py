@@ -16,7 +16,7 @@ def lorenz_batch(N, dtype=np.float32, seed=0, dev="cuda:0"):
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     r = torch.rand((N, 3), generator=g, device=dev, dtype=torch.float32).to(tdt)
     p = r * torch.tensor([10.0, 28.0, 8.0 / 3.0], device=dev, dtype=tdt)
-    prob = dg.ODEProblem(dg.models.lorenz, np.array([1, 0, 0], dtype), (0.0, 10.0),
+    prob = dg.ODEProblem(dg.models.lorenz, np.array([1, 0, 0], dtype), (0.0, float(__import__('os').environ.get('DEGK_TF', '10'))),
                          np.array([10, 28, 8 / 3], dtype))
     return prob, dg.ProblemBatch.from_arrays(prob, p=p, device=dev)
 
@@ -24,7 +24,7 @@ def lorenz_batch(N, dtype=np.float32, seed=0, dev="cuda:0"):
 def time_asolve(N, fp_mode, schedule, alg=None, reps=3, dtype=np.float32, tol=1e-6, engine="auto"):
     alg = alg or dg.GPUTsit5()
     prob, probs = lorenz_batch(N, dtype)
-    saveat = np.arange(0, 11, dtype=dtype)
+    saveat = np.linspace(0, float(__import__('os').environ.get('DEGK_TF', '10')), 11).astype(dtype)
     kw = dict(dt=dtype(0.1), saveat=saveat, abstol=dtype(tol), reltol=dtype(tol), fp_mode=fp_mode,
               schedule=schedule, stats=True, engine=engine)
     ts, us, st = dg.vectorized_asolve(probs, prob, alg, **kw)
