@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(DEGK_BLOCK) k_ode_asolve(const KArgs a) {
     ode_asolve_body<T, Model, Method<T, Model>>(a);
 }
 template <int FPMODE, class T, class Model, template <class, class> class Method, int W>
-__global__ void __launch_bounds__(DEGK_BLOCK2) k_ode_asolve2(const KArgs a) {
+// Float32: cap at 128 registers (4 blocks of 128 threads per SM).  Forcing 5 blocks (96 registers)
+// was measured slower on C2 (85 vs 92 G steps/s: the spills cost more than the extra warps hide).
+__global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? 4 : 1)) k_ode_asolve2(const KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
     ode_asolve2_body<T, Model, Method, W>(a, degk_smem);
 }
