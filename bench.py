@@ -232,7 +232,7 @@ def main():
         us_h = torch.empty((Ne, 11, 3), dtype=torch.float32, pin_memory=True)
         ts_h = torch.empty((Ne, 11), dtype=torch.float32, pin_memory=True)
         hk = dict(p=p_host, dt=f32(0.1), adaptive=True, abstol=1e-6, reltol=1e-6, saveat=SAVEAT, fp_mode=args.fp,
-                  schedule=args.schedule, out={"us": us_h, "ts": ts_h}, stats=True, device=dev, chunk_traj=1 << 22)
+                  schedule=args.schedule, out={"us": us_h, "ts": ts_h}, stats="totals", device=dev, chunk_traj=1 << 22)
         _, _, hst = dg.solve_host(prob, alg, **hk)        # warm-up (allocates workspaces)
         att_e = int(hst["totals"][0] + hst["totals"][1])
         barrier()
@@ -268,7 +268,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = (BYTES_IN + BYTES_OUT) * N / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_ode_asolve<float, Lorenz, ErkTsit5>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": ("k_ode_asolve2<float, Lorenz, ErkTsit5, W=%d>" % info.slots_per_thread2),
                 "kernel_ms": k_ms, "flops_per_attempt": F_ALG,
                 "hbm_view": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
@@ -295,7 +295,8 @@ def main():
         "config": {"workload": workload_name(N), "fp_mode": args.fp, "schedule": args.schedule,
                    "l2": "inputs (1.2 GB of parameters) and outputs (17.6 GB) exceed the 126 MB L2; no flush needed",
                    "attempted_steps_per_step": attempts_per_step, "accepted_steps_per_step": accepted_per_step,
-                   "regs_per_thread": info.regs_adaptive, "blocks_per_sm": info.max_blocks_per_sm},
+                   "regs_per_thread": info.regs_adaptive2, "blocks_per_sm": info.max_blocks_per_sm2,
+                   "trajectories_per_thread": info.slots_per_thread2, "threads_per_block": 128},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "strict_fp": other,
         "roofline": roofline, "cpu_baseline": cpu,
     }))

@@ -229,7 +229,10 @@ def solve_host(prob, alg, *, u0=None, p=None, tspan=None, n_traj=None, dt, adapt
     a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
     st = {}
-    if stats:
+    if stats == "totals":      # only the 4 global counters: no per-trajectory arrays to download
+        st = dict(totals=np.zeros(4, np.uint64))
+        a.totals = st["totals"].ctypes.data
+    elif stats:
         st = dict(retcode=np.zeros(N, np.int32), naccept=np.zeros(N, np.int32),
                   nreject=np.zeros(N, np.int32), totals=np.zeros(4, np.uint64))
         a.retcode = st["retcode"].ctypes.data; a.naccept = st["naccept"].ctypes.data
