@@ -247,6 +247,9 @@ def main():
                "note": "degk_solve_host: pinned host buffers, 4M-trajectory chunks over 3 streams; timed with the host clock around the blocking call, max over ranks"}
         del p_host, us_h, ts_h
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline (rank 0's kernel) ----

@@ -366,6 +366,10 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.dt = a->dt; k.abstol = a->abstol; k.reltol = a->reltol;
     k.seed = a->seed; k.reduce = a->reduce; k.totals = (unsigned long long*)a->totals;
     k.max_iters = a->max_iters > 0 ? a->max_iters : 1000000000LL;
+    {
+        static const int rb = getenv("DEGK_RETIRE_BATCH") ? atoi(getenv("DEGK_RETIRE_BATCH")) : 0;   // tuning knob
+        k.retire_batch = rb;
+    }
 
     const int which = (a->adaptive && !prog->is_sde) ? 1 : 0;
     int sched = a->schedule;

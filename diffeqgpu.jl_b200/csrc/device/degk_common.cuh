@@ -52,6 +52,8 @@ struct KArgs {
     u64* totals;         // optional [4]: accepted, rejected, failed, (unused)
     u64* work_counter;   // SCHED_QUEUE: next unclaimed trajectory
     i64 max_iters;
+    int retire_batch;    // v2 adaptive kernel: retire/refill when this many slots of a warp have finished
+    int reserved;
 };
 
 // ---- fused multiply-add that stays fused in both fp modes (reference: @muladd / muladd) ----
