@@ -331,6 +331,7 @@ extern "C" int64_t degk_output_rows(int dtype, double t0, double tf, double dt, 
 static int validate(degk_program* prog, const degk_solve_args* a) {
     degk_ctx* ctx = prog->ctx;
     if (a->n_traj < 0 || a->n_rows <= 0) { degk_set_error(ctx, "n_traj/n_rows invalid"); return DEGK_ERR_INVALID; }
+    if (a->n_traj == 0) return DEGK_OK;      // empty batch: nothing to check, nothing to launch
     if (!a->u0 || !a->tspan || !a->us) { degk_set_error(ctx, "u0, tspan and us are required"); return DEGK_ERR_INVALID; }
     if (prog->info.n_param > 0 && !a->p) { degk_set_error(ctx, "model has %d parameters but p is NULL", prog->info.n_param); return DEGK_ERR_INVALID; }
     if (prog->is_sde && a->adaptive) {
@@ -365,7 +366,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.retcode = a->retcode; k.naccept = a->naccept; k.nreject = a->nreject;
     k.dt = a->dt; k.abstol = a->abstol; k.reltol = a->reltol;
     k.seed = a->seed; k.reduce = a->reduce; k.totals = (unsigned long long*)a->totals;
-    k.max_iters = a->max_iters > 0 ? a->max_iters : 1000000000LL;
+    k.max_iters = a->max_iters > 0 ? a->max_iters : 10000000LL;
     {
         static const int rb = getenv("DEGK_RETIRE_BATCH") ? atoi(getenv("DEGK_RETIRE_BATCH")) : 0;   // tuning knob
         k.retire_batch = rb;

@@ -244,9 +244,7 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
         src += std::string("typedef ") + method_type(d->alg) + " METHOD;\n";
         src += std::string("template <class T_, class M_> using METHODT = ") + method_template(d->alg) + ";\n";
         src += "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
-               "    degk::ode_solve_body<REAL, MODEL, METHOD>(a);\n}\n"
-               "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_adaptive(const degk::KArgs a) {\n"
-               "    degk::ode_asolve_body<REAL, MODEL, METHOD>(a);\n}\n";
+               "    degk::ode_solve_body<REAL, MODEL, METHOD>(a);\n}\n";   // (the first-generation adaptive kernel exists ahead of time only, for A/B runs)
         snprintf(buf, sizeof buf,
                  "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
                  "extern \"C\" __global__ void __launch_bounds__(%d, (sizeof(REAL) == 4 ? 4 : 1)) degk_jit_adaptive2(const degk::KArgs a) {\n"
@@ -335,7 +333,7 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     const bool is_sde = prog->is_sde;
     CUfunction f0 = nullptr, f1 = nullptr;
     DRV(ctx, g_drv.ModuleGetFunction(&f0, mod, "degk_jit_fixed"));
-    if (!is_sde) DRV(ctx, g_drv.ModuleGetFunction(&f1, mod, "degk_jit_adaptive"));
+    // f1 (first-generation adaptive kernel) is not part of JIT builds
     prog->jit_fn[0] = f0;
     prog->jit_fn[1] = f1;
     CUfunction f2 = nullptr;

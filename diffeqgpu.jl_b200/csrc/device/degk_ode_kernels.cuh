@@ -187,6 +187,7 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                 } else {
                     store_t<T>(a, traj, 0, t0);
                     store_u<T, N>(a, traj, 0, u);
+                    fill_unwritten_ts<T>(a, traj, 1, t0);   // rows 1.. start as t0 (lowerlevel_solve.jl:318)
                 }
                 Method::init(K, u, p, t0);
                 if (!(t < tf)) {     // empty time span: nothing to integrate
@@ -236,7 +237,10 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                     T dtnew = ctl_div(h, q);
                     dtnew = jl_min(abs_(dtnew), abs_(tf - t - h));
                     const T tprev = t;
-                    const T tnew = ((tf - t - h) < Method::land()) ? tf : t + h;
+                    // a step that cannot advance t (remaining span below ulp(t)) lands on tf: the
+                    // reference would loop forever here (deviations)
+                    T tnew = ((tf - t - h) < Method::land()) ? tf : t + h;
+                    if (tnew == t) tnew = tf;
                     ++nacc;
                     Method::on_accept(K);
                     if (has_saveat) {                        // integrator_utils.jl:34-47
@@ -276,10 +280,7 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                 if (rc == RC_DEFAULT && ++iters >= a.max_iters) rc = RC_MAXITERS;
             }
             if (rc != RC_DEFAULT) {                          // retire this trajectory
-                i64 first_unwritten;
-                if (has_saveat) first_unwritten = cur - 1;
-                else first_unwritten = (rc == RC_SUCCESS && !a.save_everystep) ? 2 : 1;
-                fill_unwritten_ts<T>(a, traj, first_unwritten, t0);
+                if (has_saveat) fill_unwritten_ts<T>(a, traj, cur - 1, t0);
                 if (a.retcode) a.retcode[traj] = rc;
                 if (a.naccept) a.naccept[traj] = (int)nacc;
                 if (a.nreject) a.nreject[traj] = (int)nrej;

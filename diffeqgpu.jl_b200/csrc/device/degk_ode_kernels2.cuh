@@ -186,6 +186,9 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
             next_save2[s] = kInf;
             store_t<T>(a, claim, 0, t0_);
             store_u<T, N>(a, claim, 0, us_);
+            // without saveat only row 1 (endpoints) or the last row (first-step overshoot) can be
+            // written later: pre-fill the rest of ts with t0 now (lowerlevel_solve.jl:318 fill!)
+            fill_unwritten_ts<T>(a, claim, 1, t0_);
         }
         if (t0_ < tf_) {
             havem |= (1u << s);
@@ -226,10 +229,8 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
                             DEGK_UNROLL for (int c = 0; c < N; ++c) fin = fin && finite_(uf[c]);
                             if (!fin) rc = RC_UNSTABLE;
                         }
-                        i64 first_unwritten;
-                        if (has_saveat) first_unwritten = cur[s] - 1;
-                        else first_unwritten = (rc == RC_SUCCESS && !a.save_everystep) ? 2 : 1;
-                        fill_unwritten_ts<T>(a, traj[s], first_unwritten, ((const T*)a.tspan)[traj[s] * a.tspan_stride]);
+                        if (has_saveat)
+                            fill_unwritten_ts<T>(a, traj[s], cur[s] - 1, ((const T*)a.tspan)[traj[s] * a.tspan_stride]);
                         if (a.retcode) a.retcode[traj[s]] = rc;
                         if (a.naccept) a.naccept[traj[s]] = (int)nacc[s];
                         if (a.nreject) a.nreject[traj[s]] = (int)nrej[s];
@@ -315,7 +316,7 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
         const bool solved = MethodV::template attempt<true>(K, u, p, PO::make(tt), PO::make(hh), unew, err);
 
         // ---------------- step-size control, per slot ----------------
-        u32 accm = 0, pushm = 0, overm = 0;              // accepted / save crossing / first-step overshoot
+        u32 accm = 0, pushm = 0;                         // accepted / save crossing
         T tnew_[W];
         DEGK_UNROLL for (int s = 0; s < W; ++s) {
             // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol); ODE_DEFAULT_NORM
@@ -333,7 +334,10 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
                 accn = (c == 0) ? sq : accn + sq;
             }
             const T rem = tf[s] - t[s] - h[s];                  // tf - t - dt
-            const T tn = (rem < MethodS::land()) ? tf[s] : t[s] + h[s];
+            // a step that cannot advance t (remaining span below ulp(t)) lands on tf: the reference
+            // would loop forever here (deviations)
+            const T tsum = t[s] + h[s];
+            const T tn = ((rem < MethodS::land()) | (tsum == t[s])) ? tf[s] : tsum;
             T h_next, lq_next;
             bool reject;
 #if DEGK_STRICT
@@ -390,7 +394,6 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
             donem |= stop << s;
             failm |= fail << s;
             singm |= (live & ((u32)solved ^ 1u)) << s;
-            overm |= (finished & (u32)(!has_saveat) & (u32)(tn > tf[s])) << s;
             h[s] = ok ? h_next : h[s];
             lq[s] = ok ? lq_next : lq[s];
             t[s] = accept ? tn : t[s];
@@ -430,25 +433,8 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
             }
         }
 
-        // ---------------- first step overshoots tf (no saveat): interpolate back, kernels.jl:133-137 ----
-        if (!has_saveat) {
-            if (__any_sync(0xffffffffu, overm != 0)) {
-                DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                    if ((overm >> s) & 1u) {
-                        T up[N], ps_[NPA], un2[N], e2[N], v[N];
-                        DEGK_UNROLL for (int c = 0; c < N; ++c) up[c] = PO::get(u[c], s);
-                        DEGK_UNROLL for (int c = 0; c < NPA; ++c) ps_[c] = PO::get(p[c], s);
-                        typename MethodS::Keep Ks;
-                        MethodS::init(Ks, up, ps_, tt[s]);
-                        MethodS::template attempt<false>(Ks, up, ps_, tt[s], hh[s], un2, e2);
-                        MethodS::on_accept(Ks);
-                        MethodS::interp(Ks, (tf[s] - tt[s]) / hh[s], hh[s], up, un2, ps_, tt[s], v);
-                        store_u<T, N>(a, traj[s], a.n_rows - 1, v);
-                        store_t<T>(a, traj[s], a.n_rows - 1, tf[s]);
-                    }
-                }
-            }
-        }
+        // (kernels.jl:133-137 interpolates back when integ.t > tf.  In the adaptive path that cannot
+        //  happen: a step with t + dt >= tf always has (tf - t - dt) < 1e-14 and lands on tf.)
 
         // ---------------- commit accepted steps ----------------
         DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = blendm(accm, unew[c], u[c]);

@@ -18,6 +18,10 @@
 namespace degk {
 
 // ---------------------------------------------------------------------------------------
+// n >= 4 uses loops that are fully unrolled (register-resident LU) up to n = 8; larger systems keep
+// rolled loops (local memory) so that compile time stays bounded.
+#define DEGK_UNROLL_LU _Pragma("unroll (N <= 8 ? N : 1)")
+
 template <class T, int N>
 struct LinSolve {
     T lu[N][N];          // n>=4: L (unit, below diag) and U;  n<=3: cofactor matrix
@@ -54,31 +58,31 @@ struct LinSolve {
 #endif
             return true;
         } else {
-            DEGK_UNROLL for (int i = 0; i < N; ++i)
-                DEGK_UNROLL for (int j = 0; j < N; ++j) lu[i][j] = A[i][j];
+            DEGK_UNROLL_LU for (int i = 0; i < N; ++i)
+                DEGK_UNROLL_LU for (int j = 0; j < N; ++j) lu[i][j] = A[i][j];
             bool ok = true;
-            DEGK_UNROLL for (int k = 0; k < N; ++k) {
+            DEGK_UNROLL_LU for (int k = 0; k < N; ++k) {
                 int kp = k;
                 T amax = abs_(lu[k][k]);
-                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+                DEGK_UNROLL_LU for (int i = k + 1; i < N; ++i) {
                     const T v = abs_(lu[i][k]);
                     if (v > amax) { kp = i; amax = v; }
                 }
                 piv[k] = kp;
-                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+                DEGK_UNROLL_LU for (int i = k + 1; i < N; ++i) {
                     if (kp == i) {
-                        DEGK_UNROLL for (int j = 0; j < N; ++j) { const T s = lu[k][j]; lu[k][j] = lu[i][j]; lu[i][j] = s; }
+                        DEGK_UNROLL_LU for (int j = 0; j < N; ++j) { const T s = lu[k][j]; lu[k][j] = lu[i][j]; lu[i][j] = s; }
                     }
                 }
                 const T inv = (T)1 / lu[k][k];
                 const bool fin = finite_(inv);
-                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+                DEGK_UNROLL_LU for (int i = k + 1; i < N; ++i) {
                     const T l = fin ? lu[i][k] * inv : (T)0;
                     lu[i][k] = l;
-                    DEGK_UNROLL for (int j = k + 1; j < N; ++j) lu[i][j] = lu[i][j] - l * lu[k][j];
+                    DEGK_UNROLL_LU for (int j = k + 1; j < N; ++j) lu[i][j] = lu[i][j] - l * lu[k][j];
                 }
             }
-            DEGK_UNROLL for (int j = 0; j < N; ++j) {
+            DEGK_UNROLL_LU for (int j = 0; j < N; ++j) {
                 if (lu[j][j] == (T)0) ok = false;
                 dinv[j] = (T)1 / lu[j][j];
             }
@@ -108,19 +112,19 @@ struct LinSolve {
             }
         } else {
             T y[N];
-            DEGK_UNROLL for (int i = 0; i < N; ++i) y[i] = b[i];
-            DEGK_UNROLL for (int k = 0; k < N; ++k) {
-                DEGK_UNROLL for (int i = k + 1; i < N; ++i) {
+            DEGK_UNROLL_LU for (int i = 0; i < N; ++i) y[i] = b[i];
+            DEGK_UNROLL_LU for (int k = 0; k < N; ++k) {
+                DEGK_UNROLL_LU for (int i = k + 1; i < N; ++i) {
                     if (piv[k] == i) { const T s = y[k]; y[k] = y[i]; y[i] = s; }
                 }
             }
-            DEGK_UNROLL for (int j = 0; j < N; ++j)
-                DEGK_UNROLL for (int i = j + 1; i < N; ++i) y[i] = y[i] - lu[i][j] * y[j];
-            DEGK_UNROLL for (int j = N - 1; j >= 0; --j) {
+            DEGK_UNROLL_LU for (int j = 0; j < N; ++j)
+                DEGK_UNROLL_LU for (int i = j + 1; i < N; ++i) y[i] = y[i] - lu[i][j] * y[j];
+            DEGK_UNROLL_LU for (int j = N - 1; j >= 0; --j) {
                 y[j] = dinv[j] * y[j];
-                DEGK_UNROLL for (int i = j - 1; i >= 0; --i) y[i] = y[i] - lu[i][j] * y[j];
+                DEGK_UNROLL_LU for (int i = j - 1; i >= 0; --i) y[i] = y[i] - lu[i][j] * y[j];
             }
-            DEGK_UNROLL for (int i = 0; i < N; ++i) x[i] = y[i];
+            DEGK_UNROLL_LU for (int i = 0; i < N; ++i) x[i] = y[i];
         }
     }
 };

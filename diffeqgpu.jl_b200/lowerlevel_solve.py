@@ -153,7 +153,7 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
             a.nreject = out["nreject"].data_ptr(); a.totals = out["totals"].data_ptr()
         a.seed = int(getattr(probs, "seed", 0)) & 0xFFFFFFFFFFFFFFFF
         a.reduce = None if reduce is None else reduce.data_ptr()
-        a.max_iters = 0
+        a.max_iters = int(__import__("os").environ.get("DEGK_MAX_ITERS", "0"))   # 0 => library default (1e9)
         a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
         s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
         prog.solve(a, s)

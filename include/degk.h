@@ -153,7 +153,7 @@ typedef struct {
     double* reduce;        /* optional inout [n_rows][n_state][2]: += sum(u), sum(u^2) over the
                               trajectories of this call (SDE kernels; needs tspan_stride == 0) */
     uint64_t* totals;      /* optional inout [4]: += accepted, rejected, failed, 0 */
-    int64_t max_iters;     /* 0 => 1e9 */
+    int64_t max_iters;     /* attempts per trajectory before DEGK_RC_MAXITERS; 0 => 1e7 */
     int32_t engine;        /* degk_engine: which adaptive kernel generation to run */
     int32_t reserved;
 } degk_solve_args;

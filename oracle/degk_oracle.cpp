@@ -513,7 +513,10 @@ struct ErkInteg {
             dt = h;
             tprev = tcur;
             for (int c = 0; c < n; ++c) u[c] = unew[c];
-            if ((tf - tcur - h) < land) t = tf; else t = tcur + h;
+            // Deviation (documented in DESIGN.md): when the remaining span tf - t - dt is positive but
+            // below ulp(t), t + dt == t and the reference loops forever (dtnew is re-clamped to that
+            // remainder on every step).  A step that does not advance t is taken to land on tf.
+            if ((tf - tcur - h) < land) t = tf; else { t = tcur + h; if (t == tcur) t = tf; }
             ++naccept;
             return true;
         }
@@ -682,7 +685,7 @@ int degk_oracle_solve(int dtype, int model, int alg, int adaptive, int64_t n_tra
     a.nsave = nsave; a.fma_stages = fma_stages; a.n_traj = n_traj; a.len = len;
     a.u0_stride = u0_stride; a.p_stride = p_stride; a.tspan_stride = tspan_stride;
     a.dt = dt; a.abstol = abstol; a.reltol = reltol; a.seed = seed;
-    a.max_iters = 100000000;
+    a.max_iters = 10000000;
     if (dtype == 0)
         return solve_T<float>(a, (const float*)u0, (const float*)p, (const float*)tspan,
                               (const float*)saveat, (float*)us, (float*)ts, naccept, nreject,

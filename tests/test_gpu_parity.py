@@ -252,7 +252,7 @@ def test_jit_equals_aot(dg, alg):
     assert_bit_exact(jit2, aot, "jit(builtin) vs aot")
     prog = dg.get_program(dg.ODEProblem(dg.models.lorenz_src, U0_LORENZ.astype(f32), (0, 3), P0_LORENZ.astype(f32)),
                           getattr(dg, ALGS[alg])(), "strict")
-    assert prog.info.is_jit == 1 and prog.info.local_bytes_adaptive == 0 and prog.info.regs_adaptive > 0
+    assert prog.info.is_jit == 1 and prog.info.local_bytes_adaptive2 == 0 and prog.info.regs_adaptive2 > 0
 
 
 def test_jit_only_model_linear15_general_lu(dg, oracle):
@@ -447,3 +447,126 @@ def test_c2_million_trajectories_properties(dg, oracle):
     ts2, us2 = dg.vectorized_asolve(probs, prob, dg.GPUTsit5(), dt=f32(0.1), saveat=sv, abstol=f32(1e-6),
                                     reltol=f32(1e-6), fp_mode="strict", schedule="static")
     assert torch.equal(us2, out["strict"][0])
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases: ragged sizes, per-trajectory u0/tspan, dense saveat, kernel generations
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 31, 33, 65, 257])
+def test_sizes_not_multiple_of_warp(dg, oracle, n):
+    p = lorenz_sweep(n, seed=100 + n)
+    sv = np.arange(0, 6, dtype=f32)
+    for fp in ("strict", "fast"):
+        g = gpu_solve(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 5], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6,
+                      saveat=sv, fp_mode=fp)
+        assert (g["retcode"] == 1).all() and np.array_equal(g["ts"], np.tile(sv, (n, 1)))
+        if fp == "strict":
+            r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 5], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, saveat=sv)
+            assert_bit_exact(g, r, f"n={n}")
+    g = gpu_solve(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 5], dt=0.1)
+    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 5], dt=0.1, length=g["us"].shape[1])
+    assert_bit_exact(g, r, f"fixed n={n}")
+
+
+def test_empty_batch_is_a_no_op(dg):
+    import torch
+    prob = dg.ODEProblem(dg.models.lorenz, U0_LORENZ.astype(f32), (0.0, 1.0), P0_LORENZ.astype(f32))
+    probs = dg.ProblemBatch.from_arrays(prob, p=torch.zeros((0, 3), device="cuda:0"), n_traj=0, device="cuda:0")
+    ts, us = dg.vectorized_asolve(probs, prob, dg.GPUTsit5(), dt=f32(0.1))
+    assert ts.shape == (0, 2) and us.shape == (0, 2, 3)
+
+
+def test_per_trajectory_u0_and_tspan(dg, oracle):
+    """different initial states and time spans per trajectory (src/solve.jl:206-245 allows this
+    with saveat or endpoints-only)"""
+    n = 3000
+    rng = np.random.default_rng(8)
+    u0 = (rng.standard_normal((n, 3)) * 2).astype(f32)
+    p = lorenz_sweep(n, seed=8)
+    tspan = np.stack([np.zeros(n), rng.uniform(0.5, 6.0, n)], 1).astype(f32)
+    kw = dict(dt=0.05, adaptive=True, abstol=1e-6, reltol=1e-6)
+    g = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, save_everystep=False, **kw)
+    r = oracle.solve("lorenz", "tsit5", u0, p, tspan, save_everystep=False, **kw)
+    assert_bit_exact(g, r, "ragged tspans endpoints")
+    assert np.array_equal(g["ts"][:, 1], tspan[:, 1])
+    sv = np.array([0.0, 0.25, 0.5, 1.0, 3.0, 5.9], f32)      # some trajectories stop before the later points
+    g = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, saveat=sv, **kw)
+    r = oracle.solve("lorenz", "tsit5", u0, p, tspan, saveat=sv, **kw)
+    # rows a trajectory never reaches are left uninitialised in `us` (as in the reference, which
+    # allocates without filling, lowerlevel_solve.jl:317-323): compare the written rows only
+    written = (r["ts"] != 0)
+    written[:, 0] = True
+    g["us"] = np.where(written[:, :, None], g["us"], 0)
+    assert_bit_exact(g, r, "ragged tspans saveat")
+    short = tspan[:, 1] < 3.0
+    assert (g["ts"][short, 4] == 0).all()                    # unreached rows keep t0 (Terminated protocol)
+    g = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, dt=0.05, save_everystep=False)
+    r = oracle.solve("lorenz", "tsit5", u0, p, tspan, dt=0.05, save_everystep=False)
+    assert_bit_exact(g, r, "ragged tspans fixed dt")
+
+
+def gpu_solve_arrays(dg, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3, saveat=None,
+                     save_everystep=True, fp_mode="strict", engine="auto"):
+    import torch
+    prob = dg.ODEProblem(dg.models.lorenz, u0[0], (float(tspan[0, 0]), float(tspan[0, 1])), p[0])
+    probs = dg.ProblemBatch.from_arrays(prob, u0=u0, p=p, tspan=tspan, device="cuda:0")
+    a = getattr(dg, ALGS[alg])()
+    if adaptive:
+        ts, us, st = dg.vectorized_asolve(probs, prob, a, dt=f32(dt), abstol=f32(abstol), reltol=f32(reltol), saveat=saveat,
+                                          save_everystep=save_everystep, fp_mode=fp_mode, stats=True, engine=engine)
+    else:
+        ts, us, st = dg.vectorized_solve(probs, prob, a, dt=f32(dt), saveat=saveat, save_everystep=save_everystep,
+                                         fp_mode=fp_mode, stats=True)
+    torch.cuda.synchronize()
+    return dict(ts=ts.cpu().numpy(), us=us.cpu().numpy(), naccept=st["naccept"].cpu().numpy(),
+                nreject=st["nreject"].cpu().numpy(), retcode=st["retcode"].cpu().numpy())
+
+
+def test_dense_saveat_many_points_per_step(dg, oracle):
+    """2001 save points (> the 1024 staged in shared memory) and several per step"""
+    p = lorenz_sweep(500, seed=77)
+    sv = np.linspace(0, 10, 2001).astype(f32)
+    kw = dict(dt=0.1, adaptive=True, abstol=1e-4, reltol=1e-4, saveat=sv)
+    g = gpu_solve(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 10], **kw)
+    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 10], **kw)
+    assert_bit_exact(g, r, "dense saveat")
+    for alg in ("vern7", "rodas4"):
+        sv2 = np.linspace(0, 2, 401).astype(f32)
+        kw2 = dict(dt=0.1, adaptive=True, abstol=1e-4, reltol=1e-4, saveat=sv2)
+        g = gpu_solve(dg, "lorenz", alg, U0_LORENZ, p, [0, 2], **kw2)
+        r = oracle.solve("lorenz", alg, U0_LORENZ, p, [0, 2], **kw2)
+        assert_bit_exact(g, r, "dense saveat " + alg)
+
+
+def test_kernel_generations_agree_bitwise_in_strict_mode(dg):
+    """first-generation kernel (DEGK_ENGINE_V1) and the default second-generation kernel"""
+    n = 5000
+    rng = np.random.default_rng(3)
+    u0 = np.tile(U0_LORENZ.astype(f32), (n, 1))
+    p = lorenz_sweep(n, seed=31)
+    tspan = np.tile(np.array([0, 10], f32), (n, 1))
+    sv = np.arange(0, 11, dtype=f32)
+    kw = dict(dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, saveat=sv)
+    a = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, engine="v1", **kw)
+    b = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, engine="auto", **kw)
+    assert_bit_exact(a, b, "v1 vs v2")
+    a = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, engine="v1", dt=0.1, adaptive=True, save_everystep=False)
+    b = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, engine="auto", dt=0.1, adaptive=True, save_everystep=False)
+    assert_bit_exact(a, b, "v1 vs v2 endpoints")
+
+
+def test_initial_step_longer_than_the_span(dg, oracle):
+    """dt0 larger than the whole span.  In the adaptive path (tf - t - dt) < 1e-14 makes the step
+    land on tf (gpu_tsit5_perform_step.jl:155-156), so integ.t never exceeds tf and the
+    interpolate-back branch of kernels.jl:133-137 is not taken: the state after the full dt0 step
+    is reported at tf.  With save_everystep = true only row 1 is written."""
+    p = lorenz_sweep(200, seed=5)
+    okw = dict(dt=0.1, adaptive=True, abstol=1e-3, reltol=1e-3)
+    g = gpu_solve(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 0.05], save_everystep=False, **okw)
+    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 0.05], save_everystep=False, **okw)
+    assert_bit_exact(g, r, "dt0 > span, endpoints")
+    assert (g["ts"][:, 1] == f32(0.05)).all() and (g["naccept"] == 1).all()
+    g = gpu_solve(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 0.05], save_everystep=True, **okw)
+    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 0.05], save_everystep=True, length=2, **okw)
+    assert np.array_equal(g["ts"], r["ts"]) and np.array_equal(g["us"][:, 0], r["us"][:, 0])
+    assert (g["ts"] == 0).all()                      # nothing but row 1 is ever written
