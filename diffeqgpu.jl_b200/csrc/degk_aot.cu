@@ -18,6 +18,7 @@
 #include "device/degk_rosenbrock.cuh"
 #include "device/degk_ode_kernels.cuh"
 #include "device/degk_ode_kernels2.cuh"
+#include "device/degk_ode_kernels3.cuh"
 #include "device/degk_sde_kernels.cuh"
 #include "degk_internal.h"
 
@@ -39,7 +40,7 @@ template <int FPMODE, class T, class Model, template <class, class> class Method
 // was measured slower on C2 (85 vs 92 G steps/s: the spills cost more than the extra warps hide).
 __global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? 4 : 1)) k_ode_asolve2(const KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
-    ode_asolve2_body<T, Model, Method, W>(a, degk_smem);
+    ode_asolve_gen_body<T, Model, Method, W>(a, degk_smem);
 }
 template <int FPMODE, class T, class Model, int ALG>
 __global__ void __launch_bounds__(DEGK_BLOCK) k_sde_solve(const KArgs a) {

@@ -69,7 +69,7 @@ size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged) {
     const size_t es = dtype_size(prog->info.dtype);
     const size_t nw = DEGK_BLOCK2 / 32;
     return nw * prog->qcap2 * prog->rec_bytes2 + nw * 32 * (size_t)(prog->info.n_state + prog->info.n_param + 2) * es +
-           (size_t)n_saveat_staged * es;
+           ((size_t)n_saveat_staged + 2) * es;     // + two +inf sentinels (generation 3)
 }
 
 extern "C" int degk_version(void) { return DEGK_VERSION; }
@@ -345,6 +345,10 @@ static int validate(degk_program* prog, const degk_solve_args* a) {
     if (a->reduce && (!prog->is_sde || a->tspan_stride != 0)) {
         degk_set_error(ctx, "reduce needs an SDE program and a broadcast tspan (tspan_stride == 0)");
         return DEGK_ERR_UNSUPPORTED;
+    }
+    if (a->adaptive && a->n_traj > 2147483000LL) {
+        degk_set_error(ctx, "adaptive launches take at most 2^31 - 648 trajectories; split the batch");
+        return DEGK_ERR_INVALID;
     }
     if (a->out_layout != DEGK_LAYOUT_REF && a->out_layout != DEGK_LAYOUT_SOA) { degk_set_error(ctx, "bad out_layout"); return DEGK_ERR_INVALID; }
     return DEGK_OK;

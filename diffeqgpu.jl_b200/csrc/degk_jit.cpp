@@ -165,8 +165,7 @@ const char* builtin_struct(const char* name) {
 // host-side mirror of sizeof(degk::SaveRec<T, N>) (checked by a static_assert in the JIT source)
 static int save_rec_bytes(int dtype, int n_state) {
     const int es = dtype == DEGK_F64 ? 8 : 4;
-    int b = 8 + 4;                       // traj, cur
-    if (es == 8) b += 4;                 // padding before the first double
+    int b = 4 + 4;                       // traj, cur
     b += 3 * es + n_state * es;          // tprev, h, tnew, u[N]
     return (b + 15) / 16 * 16;           // __align__(16)
 }
@@ -179,7 +178,7 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
     src += "#include \"degk_common.cuh\"\n#include \"degk_pack.cuh\"\n";
     src += std::string("#include \"") + method_header(d->alg) + "\"\n";
     src += is_sde ? "#include \"degk_sde_kernels.cuh\"\n"
-                  : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels2.cuh\"\n";
+                  : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels2.cuh\"\n#include \"degk_ode_kernels3.cuh\"\n";
     snprintf(buf, sizeof buf, "typedef %s REAL;\n", d->dtype == DEGK_F64 ? "double" : "float");
     src += buf;
     if (d->rhs_src) {
@@ -249,7 +248,7 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                  "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
                  "extern \"C\" __global__ void __launch_bounds__(%d, (sizeof(REAL) == 4 ? 4 : 1)) degk_jit_adaptive2(const degk::KArgs a) {\n"
                  "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
-                 "    degk::ode_asolve2_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
+                 "    degk::ode_asolve_gen_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
                  save_rec_bytes(d->dtype, d->rhs_src ? d->n_state : builtin_n_state(d->builtin)), DEGK_BLOCK2, slots);
         src += buf;
     }

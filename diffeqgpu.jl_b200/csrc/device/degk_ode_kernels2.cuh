@@ -38,7 +38,7 @@ namespace degk {
 // queue record of one deferred save (lives in shared memory)
 template <class T, int N>
 struct __align__(16) SaveRec {
-    i64 traj;
+    int traj;           // index in this launch (n_traj < 2^31, checked by the host)
     int cur;            // 1-based index of the first saveat entry to write
     T tprev, h, tnew;
     T u[N];             // state at the beginning of the step
@@ -70,7 +70,7 @@ DEGK_DEV void process_saves(const KArgs& a, const SaveRec<T, Model::N>* q, int f
         T p[Model::NP > 0 ? Model::NP : 1];
         DEGK_UNROLL for (int c = 0; c < N; ++c) uprev[c] = r.u[c];
         if (Model::NP > 0) {
-            const T* pp = (const T*)a.p + r.traj * a.p_stride;
+            const T* pp = (const T*)a.p + (i64)r.traj * a.p_stride;
             DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) p[c] = pp[c];
         }
         const T tprev = r.tprev, h = r.h, tnew = r.tnew;
@@ -406,7 +406,7 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
                 const u32 pm = __ballot_sync(0xffffffffu, ps);
                 if (ps) {
                     Rec r;
-                    r.traj = traj[s];
+                    r.traj = (int)traj[s];
                     r.cur = cur[s];
                     r.tprev = tt[s];
                     r.h = hh[s];

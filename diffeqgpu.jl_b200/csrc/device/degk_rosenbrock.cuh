@@ -135,6 +135,7 @@ struct Rosenbrock23 {
     static constexpr int N = Model::N;
     static constexpr int ORDER = 2;
     static constexpr bool FSAL = false;
+    static constexpr bool ALWAYS_SOLVED = false;  // attempt() returns false when W is singular
     struct Keep { T k1[N], k2[N]; };
     static DEGK_DEV T dtmin() { return (T)1.0e-14f; }     // convert(T, 1.0f-14), SURVEY Q13
     static DEGK_DEV T land()  { return (T)1.0e-14f; }
@@ -204,6 +205,7 @@ struct Rodas {
     static constexpr int N = Model::N;
     static constexpr int ORDER = R5 ? 5 : 4;
     static constexpr bool FSAL = false;
+    static constexpr bool ALWAYS_SOLVED = false;  // attempt() returns false when W is singular
     static constexpr int NS = R5 ? 8 : 6;
     struct Keep { T ks[NS][N]; T kk[3][N]; };
     static DEGK_DEV T dtmin() { return (T)1.0e-14f; }
