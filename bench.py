@@ -243,8 +243,10 @@ def main():
         t_e = max_over_ranks(time.perf_counter() - t0, dev)
         tot_e = sum_over_ranks(att_e, dev) * args.e2e_steps
         e2e = {"value": tot_e / t_e, "unit": "trajectory-steps/s", "h2d_bytes_per_step": int(Ne * BYTES_IN + 44 + 20),
-               "d2h_bytes_per_step": int(Ne * BYTES_OUT), "traj_per_gpu": Ne, "ms_per_step": 1e3 * t_e / args.e2e_steps,
-               "note": "degk_solve_host: pinned host buffers, 4M-trajectory chunks over 3 streams; timed with the host clock around the blocking call, max over ranks"}
+               "d2h_bytes_per_step": int(Ne * (132 + 4)), "traj_per_gpu": Ne, "ms_per_step": 1e3 * t_e / args.e2e_steps,
+               "note": "degk_solve_host: pinned host buffers, 4M-trajectory chunks over 3 streams; us (132 B/trajectory) "
+                       "and one row count (4 B) come back over PCIe, the (len x N) ts array is rebuilt in host memory "
+                       "from the row counts inside the timed region; host clock around the blocking call, max over ranks"}
         del p_host, us_h, ts_h
 
     if world > 1:

@@ -61,7 +61,8 @@ class SolveArgs(C.Structure):
                 ("out_layout", C.c_int32), ("schedule", C.c_int32),
                 ("retcode", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p),
                 ("seed", C.c_uint64), ("reduce", C.c_void_p), ("totals", C.c_void_p),
-                ("max_iters", C.c_int64), ("engine", C.c_int32), ("reserved", C.c_int32)]
+                ("max_iters", C.c_int64), ("engine", C.c_int32), ("reserved", C.c_int32),
+                ("nsaved", C.c_void_p)]
 
 
 # every symbol include/degk.h declares (checked by tests/test_abi.py)

@@ -22,6 +22,10 @@
 #include "device/degk_sde_kernels.cuh"
 #include "degk_internal.h"
 
+#ifndef DEGK_A2_MINBLOCKS
+#define DEGK_A2_MINBLOCKS 4   // resident blocks per SM the Float32 adaptive kernel is compiled for (register cap 128)
+#endif
+
 namespace degk {
 
 template <class T, class M> using Rodas4M = Rodas<T, M, false>;
@@ -38,7 +42,7 @@ __global__ void __launch_bounds__(DEGK_BLOCK) k_ode_asolve(const KArgs a) {
 template <int FPMODE, class T, class Model, template <class, class> class Method, int W>
 // Float32: cap at 128 registers (4 blocks of 128 threads per SM).  Forcing 5 blocks (96 registers)
 // was measured slower on C2 (85 vs 92 G steps/s: the spills cost more than the extra warps hide).
-__global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? 4 : 1)) k_ode_asolve2(const KArgs a) {
+__global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? DEGK_A2_MINBLOCKS : 1)) k_ode_asolve2(const KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
     ode_asolve_gen_body<T, Model, Method, W>(a, degk_smem);
 }

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/degk.h"
@@ -121,6 +122,8 @@ extern "C" void degk_ctx_destroy(degk_ctx* ctx) {
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
         for (auto& w : ctx->work[i].bufs)
             if (w.ptr) cudaFree(w.ptr);
+        if (ctx->h_nsaved[i]) cudaFreeHost(ctx->h_nsaved[i]);
+        if (ctx->chunk_done[i]) cudaEventDestroy(ctx->chunk_done[i]);
     }
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_saveat) cudaFree(ctx->d_saveat);
@@ -367,7 +370,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.save_everystep = a->save_everystep ? 1 : 0;
     k.n_rows = a->n_rows; k.us = a->us; k.ts = a->ts;
     k.out_layout = a->out_layout;
-    k.retcode = a->retcode; k.naccept = a->naccept; k.nreject = a->nreject;
+    k.retcode = a->retcode; k.naccept = a->naccept; k.nreject = a->nreject; k.nsaved = a->nsaved;
     k.dt = a->dt; k.abstol = a->abstol; k.reltol = a->reltol;
     k.seed = a->seed; k.reduce = a->reduce; k.totals = (unsigned long long*)a->totals;
     k.max_iters = a->max_iters > 0 ? a->max_iters : 10000000LL;
@@ -431,8 +434,39 @@ static int ws_get(degk_ctx* ctx, int s, int slot, size_t bytes, void** out) {
     return DEGK_OK;
 }
 
-enum { WS_U0 = 0, WS_P, WS_TSPAN, WS_US, WS_TS, WS_RC, WS_NA, WS_NR, WS_REDUCE, WS_TOTALS, WS_COUNT };
+enum { WS_U0 = 0, WS_P, WS_TSPAN, WS_US, WS_TS, WS_RC, WS_NA, WS_NR, WS_REDUCE, WS_TOTALS, WS_NSAVED, WS_COUNT };
 static_assert(WS_COUNT <= DEGK_NWSBUF, "workspace slots");
+
+// Host-side rebuild of the reference's ts array for saveat runs (lowerlevel_solve.jl:318 fill! +
+// integrator_utils.jl:34-47): row k of trajectory i is saveat[k] when k < nsaved[i], else t0_i.
+// Transferring 4 bytes per trajectory instead of n_rows values cuts the D2H volume of the C2
+// sweep by 25 % (the path is PCIe-bound end to end).
+template <class T>
+static void rebuild_ts_rows(T* ts, const int32_t* nsaved, const T* saveat, const T* tspan, int64_t tspan_stride,
+                            int64_t i0, int64_t i1, int64_t rows) {
+    for (int64_t i = i0; i < i1; ++i) {
+        T* d = ts + i * rows;
+        const int64_t ns = nsaved[i - i0] < 0 ? 0 : (nsaved[i - i0] > rows ? rows : nsaved[i - i0]);
+        if (ns == rows) { memcpy(d, saveat, sizeof(T) * (size_t)rows); continue; }
+        const T t0 = tspan[i * tspan_stride];
+        for (int64_t k = 0; k < ns; ++k) d[k] = saveat[k];
+        for (int64_t k = ns; k < rows; ++k) d[k] = t0;
+    }
+}
+static void rebuild_ts(const degk_solve_args* a, size_t es, const int32_t* nsaved, int64_t c0, int64_t cn) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 4, 8), cn / 65536 + 1));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        const int64_t i0 = c0 + cn * t / nt, i1 = c0 + cn * (t + 1) / nt;
+        auto job = [=]() {
+            if (es == 4) rebuild_ts_rows<float>((float*)a->ts, nsaved + (i0 - c0), (const float*)a->saveat, (const float*)a->tspan, a->tspan_stride, i0, i1, a->n_rows);
+            else rebuild_ts_rows<double>((double*)a->ts, nsaved + (i0 - c0), (const double*)a->saveat, (const double*)a->tspan, a->tspan_stride, i0, i1, a->n_rows);
+        };
+        if (t + 1 < nt) th.emplace_back(job); else job();
+    }
+    for (auto& x : th) x.join();
+}
 
 extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int64_t chunk_traj) {
     if (!prog || !a) return DEGK_ERR_INVALID;
@@ -466,6 +500,23 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
     const size_t red_bytes = a->reduce ? sizeof(double) * a->n_rows * n * 2 : 0;
     const int nchunks = (int)((N + chunk_traj - 1) / chunk_traj);
     const int ns = std::min(DEGK_NSTREAMS, nchunks);
+    // saveat runs of the adaptive generation-2/3 kernels: ts is rebuilt on the host from the
+    // per-trajectory row counts instead of being transferred
+    const bool compact_ts = a->ts && a->saveat && a->adaptive && !prog->is_sde && a->engine != DEGK_ENGINE_V1 &&
+                            prog->info.slots_per_thread2 > 0 && a->out_layout == DEGK_LAYOUT_REF &&
+                            !getenv("DEGK_NO_COMPACT_TS");
+    if (compact_ts) {
+        const size_t need = sizeof(int32_t) * (size_t)chunk_traj;
+        for (int s = 0; s < ns; ++s) {
+            if (ctx->h_nsaved_cap[s] < need) {
+                if (ctx->h_nsaved[s]) CK(ctx, cudaFreeHost(ctx->h_nsaved[s]));
+                ctx->h_nsaved[s] = nullptr; ctx->h_nsaved_cap[s] = 0;
+                CK(ctx, cudaMallocHost((void**)&ctx->h_nsaved[s], need));
+                ctx->h_nsaved_cap[s] = need;
+            }
+            if (!ctx->chunk_done[s]) CK(ctx, cudaEventCreateWithFlags(&ctx->chunk_done[s], cudaEventDisableTiming));
+        }
+    }
     std::vector<double> red_host;
     std::vector<unsigned long long> tot_host;
     if (a->reduce) red_host.assign((size_t)ns * a->n_rows * n * 2, 0.0);
@@ -481,6 +532,11 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         cudaStream_t st = ctx->streams[s];
         const int64_t c0 = (int64_t)c * chunk_traj;
         const int64_t cn = std::min<int64_t>(chunk_traj, N - c0);
+        if (compact_ts && c >= ns) {           // chunk c - ns used this stream's row-count buffer: finish it first
+            const int64_t p0 = (int64_t)(c - ns) * chunk_traj;
+            CK(ctx, cudaEventSynchronize(ctx->chunk_done[s]));
+            rebuild_ts(a, es, ctx->h_nsaved[s], p0, std::min<int64_t>(chunk_traj, N - p0));
+        }
         degk_solve_args k = *a;
         k.n_traj = cn;
         k.traj_offset = a->traj_offset + c0;
@@ -510,8 +566,11 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         const size_t us_b = es * (size_t)cn * a->n_rows * n, ts_b = es * (size_t)cn * a->n_rows;
         rc = ws_get(ctx, s, WS_US, us_b, &dus); if (rc) return rc;
         k.us = dus;
-        if (a->ts) { rc = ws_get(ctx, s, WS_TS, ts_b, &dts); if (rc) return rc; }
+        void* dnsv = nullptr;
+        if (compact_ts) { rc = ws_get(ctx, s, WS_NSAVED, 4 * (size_t)cn, &dnsv); if (rc) return rc; }
+        else if (a->ts) { rc = ws_get(ctx, s, WS_TS, ts_b, &dts); if (rc) return rc; }
         k.ts = dts;
+        k.nsaved = (int32_t*)dnsv;
         if (a->retcode) { rc = ws_get(ctx, s, WS_RC, 4 * (size_t)cn, &drc); if (rc) return rc; }
         if (a->naccept) { rc = ws_get(ctx, s, WS_NA, 4 * (size_t)cn, &dna); if (rc) return rc; }
         if (a->nreject) { rc = ws_get(ctx, s, WS_NR, 4 * (size_t)cn, &dnr); if (rc) return rc; }
@@ -523,7 +582,8 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         // download
         if (a->out_layout == DEGK_LAYOUT_REF) {
             CK(ctx, cudaMemcpyAsync((char*)a->us + es * (size_t)c0 * a->n_rows * n, dus, us_b, cudaMemcpyDeviceToHost, st));
-            if (a->ts) CK(ctx, cudaMemcpyAsync((char*)a->ts + es * (size_t)c0 * a->n_rows, dts, ts_b, cudaMemcpyDeviceToHost, st));
+            if (compact_ts) CK(ctx, cudaMemcpyAsync(ctx->h_nsaved[s], dnsv, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
+            else if (a->ts) CK(ctx, cudaMemcpyAsync((char*)a->ts + es * (size_t)c0 * a->n_rows, dts, ts_b, cudaMemcpyDeviceToHost, st));
         } else {
             CK(ctx, cudaMemcpy2DAsync((char*)a->us + es * c0, es * N, dus, es * cn, es * cn, (size_t)a->n_rows * n, cudaMemcpyDeviceToHost, st));
             if (a->ts) CK(ctx, cudaMemcpy2DAsync((char*)a->ts + es * c0, es * N, dts, es * cn, es * cn, (size_t)a->n_rows, cudaMemcpyDeviceToHost, st));
@@ -531,6 +591,15 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         if (a->retcode) CK(ctx, cudaMemcpyAsync(a->retcode + c0, drc, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
         if (a->naccept) CK(ctx, cudaMemcpyAsync(a->naccept + c0, dna, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
         if (a->nreject) CK(ctx, cudaMemcpyAsync(a->nreject + c0, dnr, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
+        if (compact_ts) CK(ctx, cudaEventRecord(ctx->chunk_done[s], st));
+    }
+    if (compact_ts) {                           // the last min(ns, nchunks) chunks
+        for (int c = std::max(0, nchunks - ns); c < nchunks; ++c) {
+            const int s = c % ns;
+            const int64_t p0 = (int64_t)c * chunk_traj;
+            CK(ctx, cudaEventSynchronize(ctx->chunk_done[s]));
+            rebuild_ts(a, es, ctx->h_nsaved[s], p0, std::min<int64_t>(chunk_traj, N - p0));
+        }
     }
     for (int s = 0; s < ns; ++s) {
         if (a->reduce) CK(ctx, cudaMemcpyAsync(red_host.data() + (size_t)s * a->n_rows * n * 2, ctx->work[s].bufs[WS_REDUCE].ptr, red_bytes, cudaMemcpyDeviceToHost, ctx->streams[s]));

@@ -27,6 +27,10 @@ struct degk_ctx {
     cudaStream_t streams[DEGK_NSTREAMS] = {nullptr, nullptr, nullptr};
     degk_workspace work[DEGK_NSTREAMS];
     void* d_saveat = nullptr; size_t saveat_cap = 0;
+    // degk_solve_host, compact ts: pinned per-stream row-count buffers and "chunk downloaded" events
+    int32_t* h_nsaved[DEGK_NSTREAMS] = {nullptr, nullptr, nullptr};
+    size_t h_nsaved_cap[DEGK_NSTREAMS] = {0, 0, 0};
+    cudaEvent_t chunk_done[DEGK_NSTREAMS] = {nullptr, nullptr, nullptr};
 };
 
 struct degk_program {

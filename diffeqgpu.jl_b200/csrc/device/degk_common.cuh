@@ -54,6 +54,7 @@ struct KArgs {
     i64 max_iters;
     int retire_batch;    // v2 adaptive kernel: retire/refill when this many slots of a warp have finished
     int reserved;
+    int* nsaved;         // optional, per trajectory (saveat runs of the adaptive kernels): rows written
 };
 
 // ---- fused multiply-add that stays fused in both fp modes (reference: @muladd / muladd) ----

@@ -198,6 +198,10 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
             if (a.retcode) a.retcode[claim] = RC_SUCCESS;
             if (a.naccept) a.naccept[claim] = 0;
             if (a.nreject) a.nreject[claim] = 0;
+            if (has_saveat) {
+                fill_unwritten_ts<T>(a, claim, cur[s] - 1, t0_);
+                if (a.nsaved) a.nsaved[claim] = cur[s] - 1;
+            }
         }
     };
 
@@ -229,8 +233,10 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
                             DEGK_UNROLL for (int c = 0; c < N; ++c) fin = fin && finite_(uf[c]);
                             if (!fin) rc = RC_UNSTABLE;
                         }
-                        if (has_saveat)
+                        if (has_saveat) {
                             fill_unwritten_ts<T>(a, traj[s], cur[s] - 1, ((const T*)a.tspan)[traj[s] * a.tspan_stride]);
+                            if (a.nsaved) a.nsaved[traj[s]] = cur[s] - 1;
+                        }
                         if (a.retcode) a.retcode[traj[s]] = rc;
                         if (a.naccept) a.naccept[traj[s]] = (int)nacc[s];
                         if (a.nreject) a.nreject[traj[s]] = (int)nrej[s];

@@ -61,6 +61,14 @@ DEGK_DEV u32 opaque(u32 x) { asm volatile("" : "+r"(x)); return x; }
 DEGK_DEV float  lds_(u32 saddr, float)  { float v;  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr)); return v; }
 DEGK_DEV double lds_(u32 saddr, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr)); return v; }
 
+// in-place predicated increment `if (pred) ++x` as ONE predicated instruction (see assign_if)
+DEGK_DEV void inc_if(bool pred, u32& x) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(x) : "r"((u32)pred));
+}
+DEGK_DEV void inc_if(bool pred, int& x) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(x) : "r"((u32)pred));
+}
+
 template <class R>
 DEGK_DEV void rec_store_if(bool pred, u32 saddr, const R& r) {
     static_assert(sizeof(R) % 16 == 0, "SaveRec must be a multiple of 16 bytes");
@@ -129,7 +137,7 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
     T t[W], h[W], tf[W], next_save[W], next_save2[W], lq[W];   // lq: log2(N * qold^2)
     int cur[W], traj[W];
     u32 natt[W], nacc[W];
-    u32 singm = 0, multim = 0;
+    u32 singm = 0;
     DEGK_UNROLL for (int s = 0; s < W; ++s) {
         traj[s] = -1; cur[s] = 1; natt[s] = 0; nacc[s] = 0;
         t[s] = (T)0; h[s] = kDead; tf[s] = (T)0; next_save[s] = kInf; next_save2[s] = kInf; lq[s] = lqInit;
@@ -185,13 +193,17 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
             if (a.retcode) a.retcode[claim] = RC_SUCCESS;
             if (a.naccept) a.naccept[claim] = 0;
             if (a.nreject) a.nreject[claim] = 0;
-            if (has_saveat) fill_unwritten_ts<T>(a, claim, cur[s] - 1, t0_);
+            if (has_saveat) {
+                fill_unwritten_ts<T>(a, claim, cur[s] - 1, t0_);
+                if (a.nsaved) a.nsaved[claim] = cur[s] - 1;
+            }
         }
     };
 
     bool service = true;                     // warp-uniform: a slot stopped (or start of the kernel)
     u32 iter = 0;                            // warp-uniform
     bool all_done = false;
+    bool started = false;                    // warp-uniform: the first service pass (initial fill) ran
     for (;;) {
         if (service) {
             u32 freshm = 0;
@@ -205,20 +217,26 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
                 }
                 // several save points inside one accepted step: the queued record covers all of
                 // them (process_saves loops), skip the cursor past them
-                if (__any_sync(0xffffffffu, multim != 0)) {
-                    DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                        if ((multim >> s) & 1u) {
-                            while (cur[s] <= nsv && save_time(cur[s]) <= t[s]) ++cur[s];
-                            next_save[s] = save_time(cur[s]);
-                            next_save2[s] = save_time(cur[s] + 1);
-                        }
+                // (after the push next_save is the old next_save2 and t the end of the step, so
+                //  `next_save <= t` after at least one accepted step identifies exactly those slots;
+                //  before the first accepted step a save point may legitimately lie before t0 -- it
+                //  is extrapolated from the first step like integrator_utils.jl:34-47 does)
+                DEGK_UNROLL for (int s = 0; s < W; ++s) {
+                    if (next_save[s] <= t[s] && nacc[s] != 0u) {
+                        while (cur[s] <= nsv && save_time(cur[s]) <= t[s]) ++cur[s];
+                        next_save[s] = save_time(cur[s]);
+                        next_save2[s] = save_time(cur[s] + 1);
                     }
-                    multim = 0;
                 }
                 // ---------------- retire stopped trajectories, in batches ----------------
                 int ndone = 0;
                 DEGK_UNROLL for (int s = 0; s < W; ++s) ndone += __popc(__ballot_sync(0xffffffffu, (donem >> s) & 1u));
                 const bool none_live = __all_sync(0xffffffffu, havem == 0);
+                // most service entries only find fewer stopped slots than a batch: nothing to do
+                // (free slots exist only once the work queue is exhausted -- otherwise the pass
+                //  that retired them refilled them -- so there is nothing to refill either)
+                if (started && ndone < RETIRE_BATCH && !none_live) break;
+                started = true;
                 if (ndone >= RETIRE_BATCH || (ndone > 0 && none_live)) {
                     DEGK_UNROLL for (int s = 0; s < W; ++s) {
                         if ((donem >> s) & 1u) {
@@ -237,8 +255,10 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
                             else if (natt[s] >= max_it) rc = RC_MAXITERS;
                             else if (h[s] >= (T)0) rc = RC_DT_LESS_THAN_MIN;
                             else rc = RC_UNSTABLE;
-                            if (has_saveat)
+                            if (has_saveat) {
                                 fill_unwritten_ts<T>(a, traj[s], cur[s] - 1, ((const T*)a.tspan)[(i64)traj[s] * a.tspan_stride]);
+                                if (a.nsaved) a.nsaved[traj[s]] = cur[s] - 1;
+                            }
                             if (a.retcode) a.retcode[traj[s]] = rc;
                             if (a.naccept) a.naccept[traj[s]] = (int)nacc[s];
                             if (a.nreject) a.nreject[traj[s]] = (int)(natt[s] - nacc[s]);
@@ -361,8 +381,8 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
             const bool live = h[s] >= dtmin;                     // dead slots carry h < dtmin
             const bool ok = live & solved;                       // W factorised
             const bool accept = ok & !rej[s];
-            natt[s] += (u32)ok;
-            nacc[s] += (u32)accept;
+            inc_if(ok, natt[s]);
+            inc_if(accept, nacc[s]);
             const bool fin = accept & !(tn < tf[s]);
             const bool many = natt[s] >= max_it;
             // (a step size below dtmin needs no test here: the slot is simply not live any more
@@ -370,7 +390,6 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
             const bool stop = ok & (fin | many);
             const bool mult = accept & (next_save2[s] <= tn);
             push[s] = accept & (next_save[s] <= tn);
-            multim |= (u32)mult << s;
             acc_[s] = accept; ok_[s] = ok; stop_[s] = stop;
             tnew_[s] = tn;
             any_evt |= stop | mult;
@@ -396,7 +415,7 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
                 DEGK_UNROLL for (int c = 0; c < N; ++c) r.u[c] = PO::get(u[c], s);
                 rec_store_if(push[s], queue_saddr + (u32)(pos + __popc(pm & lt_mask)) * (u32)sizeof(Rec), r);
                 pos += __popc(pm);
-                cur[s] += (int)push[s];
+                inc_if(push[s], cur[s]);
                 next_save[s] = push[s] ? next_save2[s] : next_save[s];
                 next_save2[s] = save_time(cur[s] + 1);
             }
@@ -411,7 +430,9 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
             t[s] = acc_[s] ? tnew_[s] : t[s];
         }
 
-        if (qcount >= 32) {
+        // (a loop, not an `if`: up to 32 * W records can arrive in one iteration, and the queue
+        //  holds 32 + 32 * W -- it must be drained below 32 before the next push)
+        while (qcount >= 32) {
             __syncwarp();
             process_saves<T, Model, MethodS>(a, queue, qcount - 32, 32, sv);
             qcount -= 32;
@@ -419,10 +440,8 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
         }
 
         // ---------------- commit accepted steps ----------------
-        u32 accm = 0;
-        DEGK_UNROLL for (int s = 0; s < W; ++s) accm |= (u32)acc_[s] << s;
-        DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = blendm(accm, unew[c], u[c]);
-        MethodV::accepted_sel(K, accm);
+        DEGK_UNROLL for (int c = 0; c < N; ++c) assign_if(acc_, u[c], unew[c]);
+        MethodV::accepted_if(K, acc_);
 
         service = __any_sync(0xffffffffu, any_evt) | ((++iter & 255u) == 0u);
     }

@@ -41,6 +41,19 @@ DEGK_DEV Pk2 select2(bool s0, bool s1, Pk2 a, Pk2 b) { return Pk2(s0 ? a.lo() : 
 
 DEGK_DEV Pk2 blendm(unsigned m, Pk2 a, Pk2 b) { return select2((m & 1u) != 0, (m & 2u) != 0, a, b); }
 
+// In-place per-slot assignment `if (f[s]) x.slot(s) = y.slot(s)`: one predicated move per slot.
+// (Written as x = blendm(...) the compiler builds the selected pair in fresh registers and copies
+//  it back into the loop-carried pair: three instructions per slot instead of one.)
+DEGK_DEV void assign_if(const bool* f, float& x, float y)   { x = f[0] ? y : x; }
+DEGK_DEV void assign_if(const bool* f, double& x, double y) { x = f[0] ? y : x; }
+DEGK_DEV void assign_if(const bool* f, Pk2& x, Pk2 y) {
+    asm("{\n\t.reg .pred p0, p1;\n\t.reg .b32 a0, a1, b0, b1;\n\t"
+        "mov.b64 {a0, a1}, %0;\n\tmov.b64 {b0, b1}, %1;\n\t"
+        "setp.ne.u32 p0, %2, 0;\n\tsetp.ne.u32 p1, %3, 0;\n\t"
+        "@p0 mov.b32 a0, b0;\n\t@p1 mov.b32 a1, b1;\n\tmov.b64 %0, {a0, a1};\n\t}"
+        : "+l"(x.v) : "l"(y.v), "r"((unsigned)f[0]), "r"((unsigned)f[1]));
+}
+
 // PackOf<T, W>: the value type that carries W trajectories of element type T
 template <class T, int W> struct PackOf;
 template <class T> struct PackOf<T, 1> {

@@ -13,6 +13,7 @@
 // Mass matrix = identity (UniformScaling); mass-matrix/DAE problems are SURVEY §8(f) "next".
 #pragma once
 #include "degk_common.cuh"
+#include "degk_pack.cuh"
 #include "gen_rodas_consts.cuh"
 
 namespace degk {
@@ -144,6 +145,7 @@ struct Rosenbrock23 {
     static DEGK_DEV void on_accept(Keep&) {}
     static DEGK_DEV void init_sel(Keep&, const T (&)[N], const T*, T, unsigned) {}
     static DEGK_DEV void accepted_sel(Keep&, unsigned) {}
+    static DEGK_DEV void accepted_if(Keep&, const bool*) {}
 
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
@@ -214,6 +216,7 @@ struct Rodas {
     static DEGK_DEV void accepted(Keep&) {}
     static DEGK_DEV void init_sel(Keep&, const T (&)[N], const T*, T, unsigned) {}
     static DEGK_DEV void accepted_sel(Keep&, unsigned) {}
+    static DEGK_DEV void accepted_if(Keep&, const bool*) {}
 
 #define R4C(x) ((T)rodas4c::x)
 #define R5C(x) ((T)rodas5pc::x)

@@ -156,6 +156,11 @@ typedef struct {
     int64_t max_iters;     /* attempts per trajectory before DEGK_RC_MAXITERS; 0 => 1e7 */
     int32_t engine;        /* degk_engine: which adaptive kernel generation to run */
     int32_t reserved;
+    int32_t* nsaved;       /* optional out, per trajectory, saveat runs of the adaptive kernels
+                              (generation 2/3): number of leading rows written.  Rows k < nsaved
+                              hold ts = saveat[k], the others keep t0 -- which lets a caller pass
+                              ts = NULL and rebuild the reference's ts array from 4 bytes per
+                              trajectory instead of transferring it (degk_solve_host does) */
 } degk_solve_args;
 
 DEGK_API int degk_version(void);

@@ -396,6 +396,32 @@ def test_solve_host_equals_device_path(dg):
     assert np.array_equal(us2.transpose(2, 0, 1), us)
 
 
+@pytest.mark.parametrize("fp", ["strict", "fast"])
+def test_solve_host_rebuilds_ts_from_row_counts(dg, oracle, fp):
+    """degk_solve_host does not transfer ts for adaptive saveat runs: it rebuilds the reference's
+    ts array (saveat[k] for written rows, t0 for the others -- src/solve.jl:260-277 protocol) from
+    one row count per trajectory.  Per-trajectory tspans make some trajectories stop before the
+    last save points; the rebuilt array must equal the device-written one bit for bit."""
+    n = 20000
+    rng = np.random.default_rng(9)
+    p = lorenz_sweep(n, seed=12)
+    tspan = np.stack([rng.uniform(0.0, 0.4, n), rng.uniform(0.5, 6.0, n)], axis=1).astype(f32)
+    tspan[::7, 1] = tspan[::7, 0]                    # empty spans
+    sv = np.array([0.25, 1.0, 2.5, 4.0, 5.5, 7.0], f32)   # the last point is never reached
+    u0 = np.tile(U0_LORENZ.astype(f32), (n, 1))
+    prob = dg.ODEProblem(dg.models.lorenz, U0_LORENZ.astype(f32), (0.0, 6.0), P0_LORENZ.astype(f32))
+    kw = dict(dt=f32(0.1), adaptive=True, abstol=1e-5, reltol=1e-5, saveat=sv, fp_mode=fp)
+    dev = gpu_solve_arrays(dg, "tsit5", u0, p, tspan, **{k: v for k, v in kw.items() if k != "dt"}, dt=0.1)
+    ts, us, st = dg.solve_host(prob, dg.GPUTsit5(), u0=u0, p=p, tspan=tspan, chunk_traj=3000, stats=True, **kw)
+    assert np.array_equal(ts, dev["ts"])
+    written = ts != tspan[:, :1]
+    assert np.array_equal(us[written], dev["us"][written])
+    assert (ts[:, -1] == tspan[:, 0]).all() and (ts[::7] == tspan[::7, :1]).all()
+    if fp == "strict":
+        r = oracle.solve("lorenz", "tsit5", u0, p, tspan, dt=0.1, adaptive=True, abstol=1e-5, reltol=1e-5, saveat=sv)
+        assert np.array_equal(ts, r["ts"])
+
+
 def test_high_level_solve_like_public_interface(dg):
     """reference test/public_interface.jl:71-80 and gpu_ode_regression.jl:116-138"""
     prob = dg.ODEProblem(dg.models.lorenz, U0_LORENZ.astype(f32), (0.0, 10.0), P0_LORENZ.astype(f32))
