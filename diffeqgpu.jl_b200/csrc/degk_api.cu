@@ -122,9 +122,9 @@ extern "C" void degk_ctx_destroy(degk_ctx* ctx) {
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
         for (auto& w : ctx->work[i].bufs)
             if (w.ptr) cudaFree(w.ptr);
-        if (ctx->h_nsaved[i]) cudaFreeHost(ctx->h_nsaved[i]);
-        if (ctx->chunk_done[i]) cudaEventDestroy(ctx->chunk_done[i]);
     }
+    if (ctx->h_nsaved) cudaFreeHost(ctx->h_nsaved);
+    for (auto e : ctx->chunk_done) cudaEventDestroy(e);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_saveat) cudaFree(ctx->d_saveat);
     delete ctx;
@@ -505,16 +505,25 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
     const bool compact_ts = a->ts && a->saveat && a->adaptive && !prog->is_sde && a->engine != DEGK_ENGINE_V1 &&
                             prog->info.slots_per_thread2 > 0 && a->out_layout == DEGK_LAYOUT_REF &&
                             !getenv("DEGK_NO_COMPACT_TS");
+    std::thread rebuild_worker;
+    std::atomic<int> rebuild_rc{0};
+    struct Joiner {                              // every return path stops and joins the worker
+        std::thread& t; std::atomic<int>& rc; bool ok = false;
+        ~Joiner() { if (t.joinable()) { if (!ok) rc.store(2); t.join(); } }
+    } joiner{rebuild_worker, rebuild_rc};
+    ctx->chunks_enqueued.store(0);
     if (compact_ts) {
-        const size_t need = sizeof(int32_t) * (size_t)chunk_traj;
-        for (int s = 0; s < ns; ++s) {
-            if (ctx->h_nsaved_cap[s] < need) {
-                if (ctx->h_nsaved[s]) CK(ctx, cudaFreeHost(ctx->h_nsaved[s]));
-                ctx->h_nsaved[s] = nullptr; ctx->h_nsaved_cap[s] = 0;
-                CK(ctx, cudaMallocHost((void**)&ctx->h_nsaved[s], need));
-                ctx->h_nsaved_cap[s] = need;
-            }
-            if (!ctx->chunk_done[s]) CK(ctx, cudaEventCreateWithFlags(&ctx->chunk_done[s], cudaEventDisableTiming));
+        const size_t need = sizeof(int32_t) * (size_t)N;
+        if (ctx->h_nsaved_cap < need) {
+            if (ctx->h_nsaved) CK(ctx, cudaFreeHost(ctx->h_nsaved));
+            ctx->h_nsaved = nullptr; ctx->h_nsaved_cap = 0;
+            CK(ctx, cudaMallocHost((void**)&ctx->h_nsaved, need + need / 8));
+            ctx->h_nsaved_cap = need + need / 8;
+        }
+        while ((int)ctx->chunk_done.size() < nchunks) {
+            cudaEvent_t e;
+            CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->chunk_done.push_back(e);
         }
     }
     std::vector<double> red_host;
@@ -532,11 +541,6 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         cudaStream_t st = ctx->streams[s];
         const int64_t c0 = (int64_t)c * chunk_traj;
         const int64_t cn = std::min<int64_t>(chunk_traj, N - c0);
-        if (compact_ts && c >= ns) {           // chunk c - ns used this stream's row-count buffer: finish it first
-            const int64_t p0 = (int64_t)(c - ns) * chunk_traj;
-            CK(ctx, cudaEventSynchronize(ctx->chunk_done[s]));
-            rebuild_ts(a, es, ctx->h_nsaved[s], p0, std::min<int64_t>(chunk_traj, N - p0));
-        }
         degk_solve_args k = *a;
         k.n_traj = cn;
         k.traj_offset = a->traj_offset + c0;
@@ -582,7 +586,7 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         // download
         if (a->out_layout == DEGK_LAYOUT_REF) {
             CK(ctx, cudaMemcpyAsync((char*)a->us + es * (size_t)c0 * a->n_rows * n, dus, us_b, cudaMemcpyDeviceToHost, st));
-            if (compact_ts) CK(ctx, cudaMemcpyAsync(ctx->h_nsaved[s], dnsv, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
+            if (compact_ts) CK(ctx, cudaMemcpyAsync(ctx->h_nsaved + c0, dnsv, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
             else if (a->ts) CK(ctx, cudaMemcpyAsync((char*)a->ts + es * (size_t)c0 * a->n_rows, dts, ts_b, cudaMemcpyDeviceToHost, st));
         } else {
             CK(ctx, cudaMemcpy2DAsync((char*)a->us + es * c0, es * N, dus, es * cn, es * cn, (size_t)a->n_rows * n, cudaMemcpyDeviceToHost, st));
@@ -591,14 +595,25 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         if (a->retcode) CK(ctx, cudaMemcpyAsync(a->retcode + c0, drc, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
         if (a->naccept) CK(ctx, cudaMemcpyAsync(a->naccept + c0, dna, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
         if (a->nreject) CK(ctx, cudaMemcpyAsync(a->nreject + c0, dnr, 4 * (size_t)cn, cudaMemcpyDeviceToHost, st));
-        if (compact_ts) CK(ctx, cudaEventRecord(ctx->chunk_done[s], st));
-    }
-    if (compact_ts) {                           // the last min(ns, nchunks) chunks
-        for (int c = std::max(0, nchunks - ns); c < nchunks; ++c) {
-            const int s = c % ns;
-            const int64_t p0 = (int64_t)c * chunk_traj;
-            CK(ctx, cudaEventSynchronize(ctx->chunk_done[s]));
-            rebuild_ts(a, es, ctx->h_nsaved[s], p0, std::min<int64_t>(chunk_traj, N - p0));
+        if (compact_ts) {
+            CK(ctx, cudaEventRecord(ctx->chunk_done[c], st));
+            // the rebuild runs beside the transfers: a worker waits for the chunks in order
+            if (c == 0) {
+                const int dev = ctx->device;
+                rebuild_worker = std::thread([=, &rebuild_rc]() {
+                    cudaSetDevice(dev);
+                    for (int q = 0; q < nchunks; ++q) {
+                        // chunk q's event is recorded by the enqueueing thread before it moves on to
+                        // chunk q + 1; spin until it exists in the stream
+                        while (ctx->chunks_enqueued.load(std::memory_order_acquire) <= q && !rebuild_rc.load()) std::this_thread::yield();
+                        if (rebuild_rc.load()) return;
+                        if (cudaEventSynchronize(ctx->chunk_done[q]) != cudaSuccess) { rebuild_rc.store(1); return; }
+                        const int64_t p0 = (int64_t)q * chunk_traj;
+                        rebuild_ts(a, es, ctx->h_nsaved + p0, p0, std::min<int64_t>(chunk_traj, N - p0));
+                    }
+                });
+            }
+            ctx->chunks_enqueued.store(c + 1, std::memory_order_release);
         }
     }
     for (int s = 0; s < ns; ++s) {
@@ -606,6 +621,11 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         if (a->totals) CK(ctx, cudaMemcpyAsync(tot_host.data() + (size_t)s * 4, ctx->work[s].bufs[WS_TOTALS].ptr, 32, cudaMemcpyDeviceToHost, ctx->streams[s]));
     }
     for (int s = 0; s < ns; ++s) CK(ctx, cudaStreamSynchronize(ctx->streams[s]));
+    if (rebuild_worker.joinable()) {
+        joiner.ok = true;
+        rebuild_worker.join();
+        if (rebuild_rc.load()) { degk_set_error(ctx, "rebuilding ts on the host failed (CUDA event wait)"); return DEGK_ERR_CUDA; }
+    }
     if (a->reduce)
         for (int s = 0; s < ns; ++s)
             for (int64_t i = 0; i < a->n_rows * n * 2; ++i) a->reduce[i] += red_host[(size_t)s * a->n_rows * n * 2 + i];

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/degk.h"
 
@@ -28,9 +29,9 @@ struct degk_ctx {
     degk_workspace work[DEGK_NSTREAMS];
     void* d_saveat = nullptr; size_t saveat_cap = 0;
     // degk_solve_host, compact ts: pinned per-stream row-count buffers and "chunk downloaded" events
-    int32_t* h_nsaved[DEGK_NSTREAMS] = {nullptr, nullptr, nullptr};
-    size_t h_nsaved_cap[DEGK_NSTREAMS] = {0, 0, 0};
-    cudaEvent_t chunk_done[DEGK_NSTREAMS] = {nullptr, nullptr, nullptr};
+    int32_t* h_nsaved = nullptr; size_t h_nsaved_cap = 0;
+    std::vector<cudaEvent_t> chunk_done;
+    std::atomic<int> chunks_enqueued{0};
 };
 
 struct degk_program {
