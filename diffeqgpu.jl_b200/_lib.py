@@ -20,7 +20,7 @@ SCHED_STATIC, SCHED_QUEUE, SCHED_AUTO = 0, 1, 2
 NOISE_NONE, NOISE_DIAGONAL, NOISE_GENERAL = 0, 1, 2
 ENGINE_AUTO, ENGINE_V1 = 0, 1
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
-            5: "Singular"}
+            5: "Singular", 6: "Terminated"}
 
 
 class DegkError(RuntimeError):
@@ -34,7 +34,9 @@ class ModelDesc(C.Structure):
                 ("tgrad_src", C.c_char_p), ("noise_src", C.c_char_p),
                 ("n_state", C.c_int32), ("n_param", C.c_int32), ("n_noise", C.c_int32),
                 ("noise_kind", C.c_int32), ("dtype", C.c_int32), ("alg", C.c_int32),
-                ("fp_mode", C.c_int32), ("force_jit", C.c_int32)]
+                ("fp_mode", C.c_int32), ("force_jit", C.c_int32),
+                ("events", C.c_int32), ("n_callbacks", C.c_int32),
+                ("cb_condition_src", C.POINTER(C.c_char_p)), ("cb_affect_src", C.POINTER(C.c_char_p))]
 
 
 class ProgramInfo(C.Structure):
@@ -62,6 +64,7 @@ class SolveArgs(C.Structure):
                 ("retcode", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p),
                 ("seed", C.c_uint64), ("reduce", C.c_void_p), ("totals", C.c_void_p),
                 ("max_iters", C.c_int64), ("engine", C.c_int32), ("reserved", C.c_int32),
+                ("tstops", C.c_void_p), ("n_tstops", C.c_int32), ("reserved2", C.c_int32),
                 ("nsaved", C.c_void_p)]
 
 
@@ -124,9 +127,18 @@ def _b(s):
 
 def make_desc(*, builtin=None, rhs_src=None, jac_src=None, tgrad_src=None, noise_src=None,
               n_state=0, n_param=0, n_noise=0, noise_kind=NOISE_NONE, dtype=F32, alg=0,
-              fp_mode=FP_STRICT, force_jit=False):
-    return ModelDesc(_b(builtin), _b(rhs_src), _b(jac_src), _b(tgrad_src), _b(noise_src),
-                     n_state, n_param, n_noise, noise_kind, dtype, alg, fp_mode, int(force_jit))
+              fp_mode=FP_STRICT, force_jit=False, events=False, callbacks=()):
+    """callbacks: sequence of (condition_src, affect_src) CUDA-C bodies (degk.h, degk_model_desc)."""
+    d = ModelDesc(_b(builtin), _b(rhs_src), _b(jac_src), _b(tgrad_src), _b(noise_src),
+                  n_state, n_param, n_noise, noise_kind, dtype, alg, fp_mode, int(force_jit))
+    d.events = int(bool(events) or len(callbacks) > 0)
+    d.n_callbacks = len(callbacks)
+    if callbacks:
+        conds = (C.c_char_p * len(callbacks))(*[_b(c[0]) for c in callbacks])
+        affs = (C.c_char_p * len(callbacks))(*[_b(c[1]) for c in callbacks])
+        d.cb_condition_src, d.cb_affect_src = conds, affs
+        d._keepalive = (conds, affs)
+    return d
 
 
 def jit_compile_check(desc):

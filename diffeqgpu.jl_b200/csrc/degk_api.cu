@@ -182,7 +182,7 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
     memset(&prog->info, 0, sizeof prog->info);
     prog->info.dtype = d->dtype; prog->info.alg = d->alg; prog->info.fp_mode = d->fp_mode;
 
-    bool use_aot = d->builtin && !d->force_jit;
+    bool use_aot = d->builtin && !d->force_jit && !d->events && d->n_callbacks == 0;   // event kernels are JIT-built
     if (use_aot) {
         const degk_aot_entry* e0 = find_aot(d->fp_mode, d->builtin, d->alg, d->dtype, 0);
         const degk_aot_entry* e1 = is_sde ? nullptr : find_aot(d->fp_mode, d->builtin, d->alg, d->dtype, 1);
@@ -354,6 +354,10 @@ static int validate(degk_program* prog, const degk_solve_args* a) {
         return DEGK_ERR_INVALID;
     }
     if (a->out_layout != DEGK_LAYOUT_REF && a->out_layout != DEGK_LAYOUT_SOA) { degk_set_error(ctx, "bad out_layout"); return DEGK_ERR_INVALID; }
+    if (a->tstops && a->n_tstops > 0 && !prog->has_events) {
+        degk_set_error(ctx, "tstops need a program built with degk_model_desc.events = 1");
+        return DEGK_ERR_UNSUPPORTED;
+    }
     return DEGK_OK;
 }
 
@@ -371,6 +375,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.n_rows = a->n_rows; k.us = a->us; k.ts = a->ts;
     k.out_layout = a->out_layout;
     k.retcode = a->retcode; k.naccept = a->naccept; k.nreject = a->nreject; k.nsaved = a->nsaved;
+    k.tstops = a->n_tstops > 0 ? a->tstops : nullptr; k.n_tstops = a->tstops ? a->n_tstops : 0;
     k.dt = a->dt; k.abstol = a->abstol; k.reltol = a->reltol;
     k.seed = a->seed; k.reduce = a->reduce; k.totals = (unsigned long long*)a->totals;
     k.max_iters = a->max_iters > 0 ? a->max_iters : 10000000LL;
@@ -386,7 +391,8 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.schedule = sched;
 
     // second-generation adaptive kernel (deferred saves, packed pairs) unless the caller pins v1
-    const bool v2 = which == 1 && a->engine != DEGK_ENGINE_V1 && prog->info.slots_per_thread2 > 0;
+    const bool v2 = which == 1 && a->engine != DEGK_ENGINE_V1 && prog->info.slots_per_thread2 > 0 && !prog->has_events;
+    if (prog->has_events) sched = k.schedule = DEGK_SCHED_STATIC;   // one thread per trajectory
     const int block = v2 ? DEGK_BLOCK2 : DEGK_BLOCK;
     const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : DEGK_BLOCK;
     size_t smem = 0;

@@ -38,6 +38,7 @@ struct degk_program {
     degk_ctx* ctx = nullptr;
     degk_program_info info;
     bool is_sde = false;
+    bool has_events = false;                  // built with the tstops / callback kernel pair (degk_ode_events.cuh)
     const void* fn[3] = {nullptr, nullptr, nullptr};   // AOT kernels: [0] fixed-dt / SDE, [1] adaptive v1, [2] adaptive v2
     int w2 = 0, qcap2 = 0, rec_bytes2 = 0;             // geometry of the v2 kernel (see degk_internal.h)
     void* jit_module = nullptr;               // CUmodule

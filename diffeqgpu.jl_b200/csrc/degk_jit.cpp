@@ -177,8 +177,18 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
     char buf[512];
     src += "#include \"degk_common.cuh\"\n#include \"degk_pack.cuh\"\n";
     src += std::string("#include \"") + method_header(d->alg) + "\"\n";
+    const bool events = d->events != 0 || d->n_callbacks > 0;
+    if (events && (is_sde || stiff)) {
+        degk_set_error(ctx, "tstops / callbacks are available for the explicit RK solvers only");
+        return DEGK_ERR_UNSUPPORTED;
+    }
+    if (d->n_callbacks < 0 || d->n_callbacks > 16 || (d->n_callbacks > 0 && (!d->cb_condition_src || !d->cb_affect_src))) {
+        degk_set_error(ctx, "n_callbacks must be in 0..16 with condition and affect sources");
+        return DEGK_ERR_INVALID;
+    }
     src += is_sde ? "#include \"degk_sde_kernels.cuh\"\n"
-                  : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels2.cuh\"\n#include \"degk_ode_kernels3.cuh\"\n";
+           : events ? "#include \"degk_ode_events.cuh\"\n"
+                    : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels2.cuh\"\n#include \"degk_ode_kernels3.cuh\"\n";
     snprintf(buf, sizeof buf, "typedef %s REAL;\n", d->dtype == DEGK_F64 ? "double" : "float");
     src += buf;
     if (d->rhs_src) {
@@ -239,6 +249,30 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                  "    degk::sde_solve_body<REAL, MODEL, %s>(a);\n}\n",
                  d->alg == DEGK_ALG_EM ? "degk::ALG_EM" : "degk::ALG_SIEA");
         src += buf;
+    } else if (events) {
+        // callbacks: condition / affect bodies spliced into one struct (see degk_ode_events.cuh)
+        src += std::string("typedef ") + method_type(d->alg) + " METHOD;\n";
+        src += "namespace degk {\nstruct UserCallbacks {\n";
+        snprintf(buf, sizeof buf, "    static constexpr int NCB = %d;\n    static constexpr int N = MODEL::N;\n", d->n_callbacks);
+        src += buf;
+        for (int c = 0; c < d->n_callbacks; ++c) {
+            if (!d->cb_condition_src[c] || !d->cb_affect_src[c]) { degk_set_error(ctx, "callback %d: NULL source", c); return DEGK_ERR_INVALID; }
+            snprintf(buf, sizeof buf, "    template <class T> static DEGK_DEV bool condition%d(const T (&u)[N], const T* p, T t) {\n", c);
+            src += buf; src += d->cb_condition_src[c]; src += "\n    }\n";
+            snprintf(buf, sizeof buf, "    template <class T> static DEGK_DEV void affect%d(T (&u)[N], T* p, T t, bool& terminate_) {\n"
+                                      "#define terminate() (terminate_ = true)\n", c);
+            src += buf; src += d->cb_affect_src[c]; src += "\n#undef terminate\n    }\n";
+        }
+        src += "    template <class T> static DEGK_DEV bool condition(int c, const T (&u)[N], const T* p, T t) {\n        switch (c) {\n";
+        for (int c = 0; c < d->n_callbacks; ++c) { snprintf(buf, sizeof buf, "        case %d: return condition%d<T>(u, p, t);\n", c, c); src += buf; }
+        src += "        default: return false;\n        }\n    }\n";
+        src += "    template <class T> static DEGK_DEV void affect(int c, T (&u)[N], T* p, T t, bool& terminate_) {\n        switch (c) {\n";
+        for (int c = 0; c < d->n_callbacks; ++c) { snprintf(buf, sizeof buf, "        case %d: affect%d<T>(u, p, t, terminate_); break;\n", c, c); src += buf; }
+        src += "        default: break;\n        }\n    }\n};\n}\n";
+        src += "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
+               "    degk::ode_solve_events_body<REAL, MODEL, METHOD, degk::UserCallbacks>(a);\n}\n"
+               "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_adaptive(const degk::KArgs a) {\n"
+               "    degk::ode_asolve_events_body<REAL, MODEL, METHOD, degk::UserCallbacks>(a);\n}\n";
     } else {
         src += std::string("typedef ") + method_type(d->alg) + " METHOD;\n";
         src += std::string("template <class T_, class M_> using METHODT = ") + method_template(d->alg) + ";\n";
@@ -335,8 +369,15 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     // f1 (first-generation adaptive kernel) is not part of JIT builds
     prog->jit_fn[0] = f0;
     prog->jit_fn[1] = f1;
+    const bool events = d->events != 0 || d->n_callbacks > 0;
+    prog->has_events = events;
     CUfunction f2 = nullptr;
-    if (!is_sde) DRV(ctx, g_drv.ModuleGetFunction(&f2, mod, "degk_jit_adaptive2"));
+    if (events) {
+        DRV(ctx, g_drv.ModuleGetFunction(&f1, mod, "degk_jit_adaptive"));
+        prog->jit_fn[1] = f1;
+    } else if (!is_sde) {
+        DRV(ctx, g_drv.ModuleGetFunction(&f2, mod, "degk_jit_adaptive2"));
+    }
     prog->jit_fn[2] = f2;
     prog->info.is_jit = 1;
     if (d->rhs_src) {

@@ -55,6 +55,8 @@ struct KArgs {
     int retire_batch;    // v2 adaptive kernel: retire/refill when this many slots of a warp have finished
     int reserved;
     int* nsaved;         // optional, per trajectory (saveat runs of the adaptive kernels): rows written
+    const void* tstops;  // event-capable kernels (degk_ode_events.cuh): times the steppers must hit
+    int n_tstops; int reserved2;
 };
 
 // ---- fused multiply-add that stays fused in both fp modes (reference: @muladd / muladd) ----

@@ -18,6 +18,7 @@ import torch
 
 from . import _lib
 from .algorithms import (FP_MODES, SCHEDULES, GPUEM, GPUSIEA, GPUODEAlgorithm, GPUSDEAlgorithm)
+from .callbacks import as_callback_set
 from .problems import ODEProblem, ProblemBatch, SDEProblem, adapt
 
 MAX_SAVEAT_LENGTH = 100_000   # lowerlevel_solve.jl:286
@@ -80,11 +81,16 @@ def _model_key(f):
     return (f.builtin, f.rhs, f.jac, f.tgrad, f.n_state, f.n_param, f.force_jit)
 
 
-def get_program(prob, alg, fp_mode="strict", device=None):
-    """Build (or fetch) the degk_program for (model, alg, eltype, fp mode)."""
+def get_program(prob, alg, fp_mode="strict", device=None, callback=None, events=False):
+    """Build (or fetch) the degk_program for (model, alg, eltype, fp mode[, callbacks]).
+    `events` (tstops) or a non-empty callback set select the event-capable kernel pair."""
+    cbs = as_callback_set(callback)
+    events = bool(events) or len(cbs) > 0
     ctx = _lib.context(device)
     dtype = _lib.F32 if prob.dtype == np.float32 else _lib.F64
     if isinstance(prob, SDEProblem):
+        if events:
+            raise NotImplementedError("tstops / callbacks are lowered for ODE problems only")
         sf, f = prob.f, prob.f.f
         key = ("sde", _model_key(f), sf.g, sf.noise, sf.n_noise, alg.alg_id, dtype, fp_mode)
         kind = {"diagonal": _lib.NOISE_DIAGONAL, "general": _lib.NOISE_GENERAL}[sf.noise]
@@ -93,10 +99,11 @@ def get_program(prob, alg, fp_mode="strict", device=None):
                               fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit)
     else:
         f = prob.f
-        key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode)
+        key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode, events, cbs.key())
         desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, jac_src=f.jac, tgrad_src=f.tgrad,
                               n_state=f.n_state, n_param=f.n_param, dtype=dtype, alg=alg.alg_id,
-                              fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit)
+                              fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit, events=events,
+                              callbacks=cbs.key())
     return ctx.program(desc, key)
 
 
@@ -105,13 +112,14 @@ def _ptr(t):
 
 
 def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_everystep, n_rows,
-            fp_mode, schedule, layout, stats, stream, traj_offset=0, reduce=None, engine="auto"):
+            fp_mode, schedule, layout, stats, stream, traj_offset=0, reduce=None, engine="auto",
+            callback=None, tstops=None):
     if not isinstance(probs, ProblemBatch):
         probs = adapt("cuda", probs)
     dev = probs.device
     if dev.type != "cuda":
         raise RuntimeError("probs must live on a CUDA device: this engine has no CPU path")
-    prog = get_program(prob, alg, fp_mode, dev)
+    prog = get_program(prob, alg, fp_mode, dev, callback=callback, events=tstops is not None)
     n = prog.info.n_state
     N = len(probs)
     tdt = torch.float32 if prob.dtype == np.float32 else torch.float64
@@ -143,6 +151,10 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
         a.adaptive = int(adaptive)
         a.abstol = float(prob.dtype.type(abstol)); a.reltol = float(prob.dtype.type(reltol))
         a.saveat = _ptr(d_saveat); a.n_saveat = 0 if saveat is None else len(saveat)
+        d_tstops = None
+        if tstops is not None and len(tstops):
+            d_tstops = torch.as_tensor(np.asarray(tstops, dtype=prob.dtype), dtype=tdt).to(dev)   # adapt(backend, tstops)
+            a.tstops = d_tstops.data_ptr(); a.n_tstops = len(tstops)
         a.save_everystep = int(bool(save_everystep))
         a.n_rows = n_rows
         a.us = us.data_ptr(); a.ts = ts.data_ptr()
@@ -158,7 +170,7 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
         s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
         prog.solve(a, s)
         # keep inputs alive until the stream has consumed them
-        us._degk_keepalive = (probs, d_saveat)
+        us._degk_keepalive = (probs, d_saveat, d_tstops)
     if stats:
         return ts, us, out
     return ts, us
@@ -169,8 +181,6 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
                      stats=False, stream=None, traj_offset=0, reduce=None, **kwargs):
     """Fixed-step batched solve; returns (ts, us) on the device (add `stats=True` for
     per-trajectory retcode/naccept/nreject and totals, which the reference does not have)."""
-    if callback is not None or tstops is not None:
-        raise NotImplementedError("callbacks/tstops are not lowered to the C ABI yet (SURVEY §8f-2)")
     if not isinstance(alg, GPUODEAlgorithm):
         raise TypeError("alg must be a GPUODEAlgorithm / GPUSDEAlgorithm")
     is_sde = isinstance(prob, SDEProblem)
@@ -189,6 +199,11 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
         if save_everystep:
             # len = length(prob.tspan[1]:dt:prob.tspan[2])  (:71-73, :148-150)
             n_rows = int(_lib.lib().degk_output_rows(dcode, float(t0), float(tf), float(dt), 0, 1, 0))
+            if tstops is not None:
+                # len += length(tstops) - count(x -> x in tstops, timeseries)  (:74-77)
+                series = {Tt.type(t0) + Tt.type(k) * dt for k in range(n_rows)}
+                tst = [Tt.type(x) for x in tstops]
+                n_rows += len(tst) - sum(1 for x in series if x in tst)
         else:
             n_rows = 2
     else:
@@ -197,7 +212,7 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
     return _launch(probs, prob, alg, dt=dt, adaptive=False, abstol=0.0, reltol=0.0, saveat=saveat_c,
                    save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
                    schedule=schedule, layout=layout, stats=stats, stream=stream,
-                   traj_offset=traj_offset, reduce=reduce)
+                   traj_offset=traj_offset, reduce=reduce, callback=callback, tstops=tstops)
 
 
 def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save_everystep=False,
@@ -207,8 +222,6 @@ def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save
     """Adaptive batched solve (defaults as lowerlevel_solve.jl:253-260)."""
     if isinstance(prob, SDEProblem):
         raise RuntimeError("Adaptive time-stepping is not supported yet with GPUEM.")   # :348-356
-    if callback is not None or tstops is not None:
-        raise NotImplementedError("callbacks/tstops are not lowered to the C ABI yet (SURVEY §8f-2)")
     if not isinstance(alg, GPUODEAlgorithm) or isinstance(alg, GPUSDEAlgorithm):
         raise TypeError("alg must be a GPUODEAlgorithm")
     Tt = prob.dtype
@@ -225,4 +238,5 @@ def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save
         n_rows = len(saveat_c)
     return _launch(probs, prob, alg, dt=dt, adaptive=True, abstol=abstol, reltol=reltol,
                    saveat=saveat_c, save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
-                   schedule=schedule, layout=layout, stats=stats, stream=stream, engine=engine)
+                   schedule=schedule, layout=layout, stats=stats, stream=stream, engine=engine,
+                   callback=callback, tstops=tstops)

@@ -83,7 +83,8 @@ typedef enum {
     DEGK_RC_DT_LESS_THAN_MIN = 2, /* reference: device error("dt<dtmin"), gpu_tsit5_perform_step.jl:102 */
     DEGK_RC_UNSTABLE = 3,         /* non-finite state or step size */
     DEGK_RC_MAXITERS = 4,
-    DEGK_RC_SINGULAR = 5          /* reference: SingularException, linalg/lu.jl:41-44 */
+    DEGK_RC_SINGULAR = 5,         /* reference: SingularException, linalg/lu.jl:41-44 */
+    DEGK_RC_TERMINATED = 6        /* terminate!(integrator) in a callback affect, integrator_utils.jl:52-66 */
 } degk_retcode;
 
 /* DEGK_ENGINE_AUTO picks the second-generation adaptive kernel (batched deferred saves, two
@@ -112,6 +113,17 @@ typedef struct {
     int32_t alg;            /* degk_alg */
     int32_t fp_mode;        /* degk_fp_mode */
     int32_t force_jit;      /* JIT-compile even when `builtin` exists ahead of time */
+    /* Events (reference: tstops + GPUDiscreteCallback, callbacks.jl:1-36, integrator_utils.jl:69-150).
+     * events != 0 builds the event-capable kernel pair (always through NVRTC) that honours
+     * degk_solve_args.tstops and the callbacks below, explicit RK solvers only.
+     * Callback c: cb_condition_src[c] is the BODY of `bool condition(u, p, t)` (must `return`),
+     * cb_affect_src[c] the body of `affect!(integrator)`: it may assign u[i] and p[i] and call
+     * terminate().  Callbacks run in order after every step; save_positions is (false, false)
+     * like the reference requires. */
+    int32_t events;
+    int32_t n_callbacks;
+    const char* const* cb_condition_src;
+    const char* const* cb_affect_src;
 } degk_model_desc;
 
 typedef struct {
@@ -156,6 +168,11 @@ typedef struct {
     int64_t max_iters;     /* attempts per trajectory before DEGK_RC_MAXITERS; 0 => 1e7 */
     int32_t engine;        /* degk_engine: which adaptive kernel generation to run */
     int32_t reserved;
+    const void* tstops;    /* kw `tstops`: n_tstops ascending times of the program's dtype (device pointer in
+                              degk_solve, host pointer in degk_solve_host); needs a program built with
+                              events != 0 */
+    int32_t n_tstops;
+    int32_t reserved2;
     int32_t* nsaved;       /* optional out, per trajectory, saveat runs of the adaptive kernels
                               (generation 2/3): number of leading rows written.  Rows k < nsaved
                               hold ts = saveat[k], the others keep t0 -- which lets a caller pass

@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cstring>
 #include <cstdio>
+#include <limits>
 #include <vector>
 #include <algorithm>
 
@@ -331,8 +332,16 @@ struct ErkInteg {
     T t, tprev, dt, dtnew, tf, qold, abstol, reltol;
     bool u_modified;
     int naccept, nreject, nf, retcode;
+    // tstops (gpu_tsit5_perform_step.jl:18-27 fixed, :158-164 adaptive; same code in the Vern steppers)
+    const T* tstops = nullptr; int n_tstops = 0, tstops_idx = 0;
 
     inline void rhs(T* du, const T* uu, T tt) { model_f<T>(model, du, uu, p, tt); ++nf; }
+
+    // `tstops[idx] - integ.t - integ.dt - T(100) * eps(T) < T(0)` with integ.t still the old time
+    inline bool tstop_hit(T told, T h) const {
+        return n_tstops > 0 && tstops_idx < n_tstops &&
+               (tstops[tstops_idx] - told - h - (T)100 * std::numeric_limits<T>::epsilon() < (T)0);
+    }
 
     // uprev + dt*(sum a_j k_j)  -- left fold in the written order; stage 2 is (dt*a21)*k1
     // (gpu_tsit5_perform_step.jl:36-47, gpu_vern7_perform_step.jl:118-146).
@@ -468,13 +477,20 @@ struct ErkInteg {
         for (int c = 0; c < n; ++c) uprev[c] = u[c];
         T told = t;
         tprev = told;
-        t = t + dt;                               // integ.t += dt (before the stages)
+        T h = dt;                                 // local dt: integ.dt keeps the nominal step
+        if (tstop_hit(told, dt)) {
+            t = tstops[tstops_idx];
+            h = t - tprev;
+            ++tstops_idx;
+        } else {
+            t = t + dt;                           // integ.t += dt (before the stages)
+        }
         if (tab->fsal) {
             if (u_modified) { rhs(k[1], uprev, told); u_modified = false; }
             else for (int c = 0; c < n; ++c) k[1][c] = k[tab->stages][c];
         }
         T unew[MAXN];
-        stages(dt, told, unew);
+        stages(h, told, unew);
         for (int c = 0; c < n; ++c) u[c] = unew[c];
         ++naccept;
     }
@@ -516,7 +532,15 @@ struct ErkInteg {
             // Deviation (documented in DESIGN.md): when the remaining span tf - t - dt is positive but
             // below ulp(t), t + dt == t and the reference loops forever (dtnew is re-clamped to that
             // remainder on every step).  A step that does not advance t is taken to land on tf.
-            if ((tf - tcur - h) < land) t = tf; else { t = tcur + h; if (t == tcur) t = tf; }
+            if ((tf - tcur - h) < land) t = tf;
+            else if (tstop_hit(tcur, h)) {
+                // integ.t = tstop; integ.u = integ(integ.t)  (dense output of the step just taken)
+                t = tstops[tstops_idx];
+                T v[MAXN];
+                interpolant((t - tprev) / dt, dt, v);
+                for (int c = 0; c < n; ++c) u[c] = v[c];
+                ++tstops_idx;
+            } else { t = tcur + h; if (t == tcur) t = tf; }
             ++naccept;
             return true;
         }
@@ -543,8 +567,41 @@ struct SolveArgs {
     double dt, abstol, reltol;
     uint64_t seed;
     int64_t max_iters;
+    // events: tstops and discrete callbacks given as small specs that the tests
+    // also lower to CUDA-C source for the device (tests/cases.py)
+    int n_tstops = 0; const double* tstops = nullptr;
+    int n_cb = 0; const int32_t* cb_i = nullptr; const double* cb_v = nullptr;
 };
 
+// condition kinds: 0 t == v | 1 u[i] < v | 2 u[i] > v | 3 t >= v
+// affect kinds:    0 u[i] += v | 1 u[i] = v | 2 u[i] *= v | 3 terminate!(integrator) | 4 p[i] = v
+template <class T>
+inline bool cb_condition(const SolveArgs& a, int c, const T* u, const T* p, T t) {
+    (void)p;
+    const int kind = a.cb_i[4 * c], idx = a.cb_i[4 * c + 1];
+    const T v = (T)a.cb_v[2 * c];
+    switch (kind) {
+    case 0: return t == v;
+    case 1: return u[idx] < v;
+    case 2: return u[idx] > v;
+    default: return t >= v;
+    }
+}
+template <class T>
+inline void cb_affect(const SolveArgs& a, int c, T* u, T* p, T t, bool& terminated) {
+    (void)t;
+    const int kind = a.cb_i[4 * c + 2], idx = a.cb_i[4 * c + 3];
+    const T v = (T)a.cb_v[2 * c + 1];
+    switch (kind) {
+    case 0: u[idx] = u[idx] + v; break;
+    case 1: u[idx] = v; break;
+    case 2: u[idx] = u[idx] * v; break;
+    case 3: terminated = true; break;
+    default: p[idx] = v; break;
+    }
+}
+
+enum { RC_TERMINATED = 6 };   // ReturnCode.Terminated (terminate! in an affect, integrator_utils.jl:52-66)
 enum AlgId { A_TSIT5 = 0, A_VERN7 = 1, A_VERN9 = 2, A_ROS23 = 3, A_RODAS4 = 4, A_RODAS5P = 5,
              A_EM = 6, A_SIEA = 7 };
 
@@ -564,23 +621,42 @@ void drive(Integ& I, const SolveArgs& a, int order, T t0, T tf, const T* u0, con
     }
     step_idx += 1;
     int64_t iters = 0;
+    bool terminated = false;
+    // savevalues! (integrator_utils.jl:13-50); adaptive integrators carry save_everystep = false (Q3)
+    auto savevalues = [&]() {
+        if (!has_saveat && a.save_everystep && !a.adaptive) {
+            out.put_u(step_idx - 1, I.u);
+            out.put_t(step_idx - 1, I.t);
+            ++step_idx;
+        } else if (has_saveat) {
+            savevalues_saveat<T>(I, out, saveat, a.nsave, cur_t);
+        }
+    };
+    // handle_callbacks! -> apply_discrete_callback! (integrator_utils.jl:69-96, 271-330): each
+    // callback whose condition holds saves first, then sets u_modified and runs its affect
+    auto callbacks = [&]() -> bool {
+        bool saved_in_cb = false;
+        for (int c = 0; c < a.n_cb; ++c) {
+            if (cb_condition<T>(a, c, I.u, I.p, I.t)) {
+                savevalues();
+                saved_in_cb = true;
+                I.u_modified = true;
+                cb_affect<T>(a, c, I.u, I.p, I.t, terminated);
+            }
+        }
+        return saved_in_cb;
+    };
     if (a.adaptive) {
         Controller<T> C(order);
-        while (I.t < tf) {
+        while (I.t < tf && !terminated) {
             if (!I.step_adaptive(C)) return;
-            if (has_saveat) savevalues_saveat<T>(I, out, saveat, a.nsave, cur_t);
+            if (!callbacks()) savevalues();
             if (++iters >= a.max_iters) { I.retcode = RC_MAXITERS; return; }
         }
     } else {
-        while (I.t < tf) {
+        while (I.t < tf && !terminated) {
             I.step_fixed();
-            if (!has_saveat && a.save_everystep) {
-                out.put_u(step_idx - 1, I.u);
-                out.put_t(step_idx - 1, I.t);
-                ++step_idx;
-            } else if (has_saveat) {
-                savevalues_saveat<T>(I, out, saveat, a.nsave, cur_t);
-            }
+            if (!callbacks()) savevalues();
             if (++iters >= a.max_iters) { I.retcode = RC_MAXITERS; return; }
         }
     }
@@ -599,7 +675,7 @@ void drive(Integ& I, const SolveArgs& a, int order, T t0, T tf, const T* u0, con
     }
     bool finite = true;
     for (int c = 0; c < I.n; ++c) if (!(I.u[c] == I.u[c]) || std::isinf((double)I.u[c])) finite = false;
-    I.retcode = finite ? RC_SUCCESS : RC_UNSTABLE;
+    I.retcode = terminated ? (int)RC_TERMINATED : (finite ? (int)RC_SUCCESS : (int)RC_UNSTABLE);
 }
 
 #include "oracle_stiff.inc"
@@ -625,6 +701,9 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
+    std::vector<T> tstops_T(a.n_tstops);
+    for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
+    if ((a.n_tstops > 0 || a.n_cb > 0) && !tab) return -3;   // events: explicit RK steppers only
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < a.n_traj; ++i) {
         const T* ui = u0 + i * a.u0_stride;
@@ -641,6 +720,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
             I.t = t0; I.tprev = t0; I.dt = (T)a.dt; I.dtnew = (T)a.dt; I.tf = tf;
             I.qold = (T)1.0e-4; I.abstol = (T)a.abstol; I.reltol = (T)a.reltol;
             I.u_modified = true; I.naccept = I.nreject = I.nf = 0; I.retcode = RC_DEFAULT;
+            I.tstops = tstops_T.empty() ? nullptr : tstops_T.data(); I.n_tstops = (int)tstops_T.size(); I.tstops_idx = 0;
             drive<T>(I, a, order, t0, tf, ui, out, saveat);
             na = I.naccept; nr = I.nreject; rc = I.retcode;
         } else if (a.alg == A_ROS23 || a.alg == A_RODAS4 || a.alg == A_RODAS5P) {
@@ -686,6 +766,34 @@ int degk_oracle_solve(int dtype, int model, int alg, int adaptive, int64_t n_tra
     a.u0_stride = u0_stride; a.p_stride = p_stride; a.tspan_stride = tspan_stride;
     a.dt = dt; a.abstol = abstol; a.reltol = reltol; a.seed = seed;
     a.max_iters = 10000000;
+    if (dtype == 0)
+        return solve_T<float>(a, (const float*)u0, (const float*)p, (const float*)tspan,
+                              (const float*)saveat, (float*)us, (float*)ts, naccept, nreject,
+                              retcode, nthreads);
+    return solve_T<double>(a, (const double*)u0, (const double*)p, (const double*)tspan,
+                           (const double*)saveat, (double*)us, (double*)ts, naccept, nreject,
+                           retcode, nthreads);
+}
+
+// same solve with events: tstops (Float64 values, converted to the dtype) and discrete callbacks
+// cb_i[4*c + {0,1,2,3}] = condition kind, condition index, affect kind, affect index;
+// cb_v[2*c + {0,1}] = condition value, affect value
+int degk_oracle_solve_events(int dtype, int model, int alg, int adaptive, int64_t n_traj,
+                             const void* u0, int64_t u0_stride, const void* p, int64_t p_stride,
+                             const void* tspan, int64_t tspan_stride,
+                             double dt, double abstol, double reltol,
+                             const void* saveat, int nsave, int save_everystep, uint64_t seed,
+                             void* us, void* ts, int64_t len,
+                             int32_t* naccept, int32_t* nreject, int32_t* retcode,
+                             int fma_stages, int nthreads,
+                             const double* tstops, int n_tstops, const int32_t* cb_i, const double* cb_v, int n_cb) {
+    SolveArgs a;
+    a.model = model; a.alg = alg; a.adaptive = adaptive; a.save_everystep = save_everystep;
+    a.nsave = nsave; a.fma_stages = fma_stages; a.n_traj = n_traj; a.len = len;
+    a.u0_stride = u0_stride; a.p_stride = p_stride; a.tspan_stride = tspan_stride;
+    a.dt = dt; a.abstol = abstol; a.reltol = reltol; a.seed = seed;
+    a.max_iters = 10000000;
+    a.tstops = tstops; a.n_tstops = n_tstops; a.cb_i = cb_i; a.cb_v = cb_v; a.n_cb = n_cb;
     if (dtype == 0)
         return solve_T<float>(a, (const float*)u0, (const float*)p, (const float*)tspan,
                               (const float*)saveat, (float*)us, (float*)ts, naccept, nreject,

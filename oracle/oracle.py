@@ -18,7 +18,10 @@ MODELS = {"lorenz": 0, "henon_heiles": 1, "rober": 2, "decay": 3, "linear15": 4,
 ALGS = {"tsit5": 0, "vern7": 1, "vern9": 2, "rosenbrock23": 3, "rodas4": 4, "rodas5p": 5,
         "em": 6, "siea": 7}
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
-            5: "Singular"}
+            5: "Singular", 6: "Terminated"}
+# discrete-callback specs shared with tests/cases.py (which lowers them to CUDA-C for the device)
+COND_KINDS = {"t_eq": 0, "u_lt": 1, "u_gt": 2, "t_ge": 3}
+AFFECT_KINDS = {"u_add": 0, "u_set": 1, "u_scale": 2, "terminate": 3, "p_set": 4}
 
 _lib = None
 
@@ -47,6 +50,9 @@ def lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_int, ctypes.c_int]
+        _lib.degk_oracle_solve_events.restype = ctypes.c_int
+        _lib.degk_oracle_solve_events.argtypes = _lib.degk_oracle_solve.argtypes + [
+            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _lib.degk_oracle_num_threads.restype = ctypes.c_int
     return _lib
 
@@ -64,12 +70,15 @@ def _ptr(a):
 
 def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3,
           saveat=None, save_everystep=True, length=None, seed=0, dtype=np.float32,
-          fma_stages=False, nthreads=0):
+          fma_stages=False, nthreads=0, tstops=None, callbacks=()):
     """Solve a batch; returns dict(ts=(N,len), us=(N,len,n), naccept, nreject, retcode).
 
     u0: (N,n) or (n,) broadcast; p: (N,np) or (np,) broadcast; tspan: (2,) or (N,2).
     `length` = number of output rows (the host-side `len` of lowerlevel_solve.jl); required
     unless saveat is given (-> len(saveat)) or endpoints-only (-> 2).
+    tstops: times the steppers must hit; callbacks: sequence of
+    ((cond_kind, cond_idx, cond_val), (affect_kind, affect_idx, affect_val)) discrete callbacks
+    (kinds: COND_KINDS / AFFECT_KINDS), applied in order after every step.
     """
     dtype = np.dtype(dtype)
     n, npar, _, _ = model_info(model)
@@ -96,12 +105,22 @@ def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1
     na = np.zeros(N, np.int32)
     nr = np.zeros(N, np.int32)
     rc = np.zeros(N, np.int32)
-    r = lib().degk_oracle_solve(
-        0 if dtype == np.float32 else 1, MODELS[model], ALGS[alg], int(adaptive), N,
-        _ptr(u0), u0s, _ptr(p), ps, _ptr(tspan), tss,
-        float(dtype.type(dt)), float(dtype.type(abstol)), float(dtype.type(reltol)),
-        _ptr(saveat), 0 if saveat is None else len(saveat), int(save_everystep), int(seed),
-        _ptr(us), _ptr(ts), length, _ptr(na), _ptr(nr), _ptr(rc), int(fma_stages), int(nthreads))
+    args = [0 if dtype == np.float32 else 1, MODELS[model], ALGS[alg], int(adaptive), N,
+            _ptr(u0), u0s, _ptr(p), ps, _ptr(tspan), tss,
+            float(dtype.type(dt)), float(dtype.type(abstol)), float(dtype.type(reltol)),
+            _ptr(saveat), 0 if saveat is None else len(saveat), int(save_everystep), int(seed),
+            _ptr(us), _ptr(ts), length, _ptr(na), _ptr(nr), _ptr(rc), int(fma_stages), int(nthreads)]
+    if tstops is not None or len(callbacks):
+        # tstops reach the integrator already converted to the time type (adapt(backend, tstops))
+        tst = np.ascontiguousarray([] if tstops is None else np.asarray(tstops, dtype=dtype), dtype=np.float64)
+        cb_i = np.zeros((max(len(callbacks), 1), 4), np.int32)
+        cb_v = np.zeros((max(len(callbacks), 1), 2), np.float64)
+        for c, ((ck, ci, cv), (ak, ai, av)) in enumerate(callbacks):
+            cb_i[c] = (COND_KINDS[ck], ci, AFFECT_KINDS[ak], ai)
+            cb_v[c] = (float(dtype.type(cv)), float(dtype.type(av)))
+        r = lib().degk_oracle_solve_events(*args, _ptr(tst), len(tst), _ptr(cb_i), _ptr(cb_v), len(callbacks))
+    else:
+        r = lib().degk_oracle_solve(*args)
     if r != 0:
         raise RuntimeError(f"oracle error {r}")
     return dict(ts=ts, us=us, naccept=na, nreject=nr, retcode=rc)

@@ -45,3 +45,23 @@ def golden_cases():
         cases.append((f"gbm_{alg}_f32", dict(model="gbm", alg=alg, u0=np.full((32, 3), 0.1), p=[1.5, 0.01], tspan=[0, 1], dt=1 / 64, save_everystep=False, seed=1234, dtype=f32)))
     cases.append(("lorenz_additive_em_saveat_f32", dict(model="lorenz_additive", alg="em", u0=U0_LORENZ, p=lorenz_sweep(8), tspan=[0, 1], dt=1e-3, saveat=[0.0, 0.25, 0.5, 1.0], seed=7, dtype=f32)))
     return cases
+
+
+# ------------------------------------------------------------------------------------------
+# discrete-callback specs: one description, two lowerings -- the oracle interprets the spec
+# (oracle.COND_KINDS / AFFECT_KINDS), the device gets CUDA-C bodies (include/degk.h,
+# degk_model_desc.cb_condition_src / cb_affect_src)
+# ------------------------------------------------------------------------------------------
+def _lit(v, dtype):
+    return f"(T){float(np.dtype(dtype).type(v))!r}"
+
+
+def callback_sources(spec, dtype=np.float32):
+    """spec: ((cond_kind, idx, val), (affect_kind, idx, val)) -> (condition_src, affect_src)"""
+    (ck, ci, cv), (ak, ai, av) = spec
+    cond = {"t_eq": f"return t == {_lit(cv, dtype)};", "u_lt": f"return u[{ci}] < {_lit(cv, dtype)};",
+            "u_gt": f"return u[{ci}] > {_lit(cv, dtype)};", "t_ge": f"return t >= {_lit(cv, dtype)};"}[ck]
+    aff = {"u_add": f"u[{ai}] = u[{ai}] + {_lit(av, dtype)};", "u_set": f"u[{ai}] = {_lit(av, dtype)};",
+           "u_scale": f"u[{ai}] = u[{ai}] * {_lit(av, dtype)};", "terminate": "terminate();",
+           "p_set": f"p[{ai}] = {_lit(av, dtype)};"}[ak]
+    return cond, aff

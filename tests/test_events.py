@@ -1,0 +1,288 @@
+"""tstops + discrete callbacks: oracle against the reference's own test
+assertions (test/gpu_kernel_de/gpu_ode_discrete_callbacks.jl, with the exact solution standing
+in for OrdinaryDiffEq), the NVRTC lowering of callback bodies, and -- on the GPU -- bit parity of
+the event-capable kernels (degk_ode_events.cuh) with the oracle."""
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from cases import P0_LORENZ, U0_LORENZ, callback_sources, lorenz_sweep  # noqa: E402
+
+f32, f64 = np.float32, np.float64
+KICK = (("t_eq", 0, 2.4), ("u_add", 0, 10.0))          # condition(u,t,integ) = t == 2.4f0; affect!: u += 10
+KICK4 = (("t_eq", 0, 4.0), ("u_add", 0, 10.0))
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle
+    return oracle
+
+
+def exact_decay_with_kicks(t, kicks, u0=10.0):
+    """du = -u with u += 10 at the kick times (value AFTER the kick at the kick time itself)"""
+    u, tl = u0, 0.0
+    for tk in sorted(kicks):
+        if t < tk:
+            break
+        u = u * math.exp(-(tk - tl)) + 10.0
+        tl = tk
+    return u * math.exp(-(t - tl))
+
+
+# ------------------------------------------------------------------------------------------
+# oracle against the reference tests' assertions (gpu_ode_discrete_callbacks.jl:26-140)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "vern9"])
+def test_oracle_fixed_dt_tstops_and_kick(oracle, alg):
+    # "Unadaptive version": dt = 1, tstops = [2.4], every-step saves
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=1.0, length=12, tstops=[2.4], callbacks=[KICK])
+    ts, us = r["ts"][0], r["us"][0, :, 0]
+    assert np.allclose(ts, [0, 1, 2, 2.4, 3.4, 4.4, 5.4, 6.4, 7.4, 8.4, 9.4, 10], atol=1e-6)
+    # the callback saves BEFORE its affect (apply_discrete_callback!): the row at 2.4 is pre-kick
+    assert abs(us[3] - 10 * math.exp(-2.4)) < 2e-3
+    exact = np.array([exact_decay_with_kicks(t, [2.4]) for t in ts])
+    exact[3] = 10 * math.exp(-2.4)
+    assert np.linalg.norm(us - exact) < (5e-3 if alg != "tsit5" else 6e-2)   # dt = 1: Tsit5 truncation error
+    # floating-point truncation when adjusting t for tstops (dt = 0.01, tstop 4.0): :43-60
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.01, length=1001, tstops=[4.0], callbacks=[KICK4])
+    ts, us = r["ts"][0], r["us"][0, :, 0]
+    k = int(np.argmin(np.abs(ts - 4.0)))
+    assert ts[k] == f32(4.0)
+    assert abs(us[k + 1] - exact_decay_with_kicks(float(ts[k + 1]), [4.0])) < 3e-5
+    assert abs(us[-1] - exact_decay_with_kicks(float(ts[-1]), [4.0])) < 3e-5
+
+
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "vern9"])
+def test_oracle_callback_set_saveat_and_endpoints(oracle, alg):
+    cbs = [KICK, KICK4]
+    kw = dict(dt=1.0, tstops=[2.4, 4.0], callbacks=cbs)
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], length=13, **kw)
+    assert np.allclose(r["ts"][0][:6], [0, 1, 2, 2.4, 3.4, 4.0], atol=1e-6)
+    # saveat = [0, 6]
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], saveat=np.array([0.0, 6.0], f32), **kw)
+    assert abs(r["us"][0, 1, 0] - exact_decay_with_kicks(6.0, [2.4, 4.0])) < (3e-3 if alg != "tsit5" else 3e-2)
+    # save_everystep = false: row 2 is the raw final state
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], save_everystep=False, **kw)
+    assert abs(r["us"][0, 1, 0] - exact_decay_with_kicks(float(r["ts"][0, 1]), [2.4, 4.0])) < (2e-4 if alg != "tsit5" else 2e-2)
+
+
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "vern9"])
+def test_oracle_adaptive_tstops_kick_and_terminate(oracle, alg):
+    kw = dict(dt=1.0, adaptive=True, abstol=1e-7, reltol=1e-7)
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], save_everystep=False, tstops=[4.0], callbacks=[KICK4], **kw)
+    assert r["ts"][0, 1] == f32(10.0) and r["retcode"][0] == 1
+    assert abs(r["us"][0, 1, 0] - exact_decay_with_kicks(10.0, [4.0])) < 2e-5
+    sv = np.arange(0, 11, dtype=f32)
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], saveat=sv, tstops=[4.0], callbacks=[KICK4], **kw)
+    exact = np.array([exact_decay_with_kicks(t, [4.0]) for t in sv])
+    exact[4] = 10 * math.exp(-4.0)                       # saved before the affect
+    assert np.abs(r["us"][0, :, 0] - exact).max() < 2e-4      # dense output of large Vern9 steps
+    # terminate!(integrator) once u < 1: later rows keep t0, retcode Terminated
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], saveat=sv, callbacks=[(("u_lt", 0, 1.0), ("terminate", 0, 0.0))], **kw)
+    assert r["retcode"][0] == 6
+    assert (r["ts"][0, :3] == sv[:3]).all() and (r["ts"][0, 3:] == 0).all()     # u(2.3) = 1.0026, u(3) < 1
+    assert np.abs(r["us"][0, :3, 0] - 10 * np.exp(-sv[:3])).max() < 2e-4
+
+
+def test_oracle_without_events_is_unchanged(oracle):
+    """the events entry point with no tstops/callbacks reproduces the committed golden vectors"""
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "oracle_golden.npz")
+    p = lorenz_sweep(64, seed=3)
+    sv = np.arange(0, 6, dtype=f32)
+    a = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 5], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, saveat=sv)
+    b = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 5], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, saveat=sv,
+                     tstops=[])
+    assert np.array_equal(a["us"], b["us"]) and np.array_equal(a["naccept"], b["naccept"])
+    assert len(gold.files) > 0
+
+
+# ------------------------------------------------------------------------------------------
+# host logic (no GPU): lowering of the callback bodies, argument checks
+# ------------------------------------------------------------------------------------------
+def test_callback_bodies_compile_with_nvrtc():
+    import diffeqgpu_b200 as dg
+    from diffeqgpu_b200 import _lib
+    specs = [KICK, (("u_lt", 0, 0.5), ("terminate", 0, 0.0)), (("t_ge", 0, 5.0), ("p_set", 0, 2.0))]
+    for alg in (dg.GPUTsit5(), dg.GPUVern7(), dg.GPUVern9()):
+        for dtype in (_lib.F32, _lib.F64):
+            for fp in (_lib.FP_STRICT, _lib.FP_FAST):
+                d = _lib.make_desc(builtin="decay", dtype=dtype, alg=alg.alg_id, fp_mode=fp,
+                                   callbacks=[callback_sources(s) for s in specs])
+                st, nbytes, log = _lib.jit_compile_check(d)
+                assert st == 0 and nbytes > 0, log
+    # tstops without callbacks: events flag only
+    st, nbytes, log = _lib.jit_compile_check(_lib.make_desc(builtin="lorenz", dtype=_lib.F32, alg=0, events=True))
+    assert st == 0, log
+    # stiff solvers: not lowered
+    st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="rober", dtype=_lib.F32, alg=5, events=True))
+    assert st != 0 and "explicit RK" in log
+    # a broken body reports the NVRTC log
+    st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="decay", dtype=_lib.F32, alg=0,
+                                                       callbacks=[("return t == ;", "u[0] = 1;")]))
+    assert st != 0 and "error" in log
+
+
+def test_callback_argument_checks():
+    import diffeqgpu_b200 as dg
+    with pytest.raises(ValueError, match="save_positions"):
+        dg.DiscreteCallback("return true;", "", save_positions=(True, True))       # callbacks.jl:12-14
+    with pytest.raises(NotImplementedError):
+        dg.ContinuousCallback("return u[0];", "")
+    cs = dg.CallbackSet(dg.DiscreteCallback("return true;", "u[0] = 0;"), None,
+                        dg.CallbackSet(dg.DiscreteCallback("return false;", "")))
+    assert len(cs) == 2
+
+
+# ------------------------------------------------------------------------------------------
+# GPU: the event kernels against the oracle, bit for bit in strict mode
+# ------------------------------------------------------------------------------------------
+ALGS = {"tsit5": "GPUTsit5", "vern7": "GPUVern7", "vern9": "GPUVern9"}
+
+
+def gpu_events(dg, model, alg, u0, p, tspan, specs, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3, saveat=None,
+               save_everystep=True, tstops=None, dtype=f32, fp_mode="strict"):
+    import torch
+    f = getattr(dg.models, model)
+    u0 = np.asarray(u0, dtype)
+    p = np.asarray(p, dtype)
+    prob = dg.ODEProblem(f, u0[0] if u0.ndim == 2 else u0, tuple(tspan), p[0] if p.ndim == 2 else p)
+    n = max(u0.shape[0] if u0.ndim == 2 else 1, p.shape[0] if p.ndim == 2 else 1)
+    probs = dg.ProblemBatch.from_arrays(prob, u0=u0 if u0.ndim == 2 else None, p=p if p.ndim == 2 else None,
+                                        n_traj=n, device="cuda:0")
+    cb = dg.CallbackSet(*[dg.DiscreteCallback(*callback_sources(s, dtype)) for s in specs]) if specs else None
+    a = getattr(dg, ALGS[alg])()
+    kw = dict(dt=dtype(dt), saveat=saveat, save_everystep=save_everystep, callback=cb, tstops=tstops, fp_mode=fp_mode, stats=True)
+    if adaptive:
+        ts, us, st = dg.vectorized_asolve(probs, prob, a, abstol=dtype(abstol), reltol=dtype(reltol), **kw)
+    else:
+        ts, us, st = dg.vectorized_solve(probs, prob, a, **kw)
+    torch.cuda.synchronize()
+    return dict(ts=ts.cpu().numpy(), us=us.cpu().numpy(), naccept=st["naccept"].cpu().numpy(),
+                nreject=st["nreject"].cpu().numpy(), retcode=st["retcode"].cpu().numpy())
+
+
+def assert_same(g, r, what, written_only=False):
+    assert np.array_equal(g["ts"], r["ts"]), f"{what}: ts differs"
+    for k in ("naccept", "nreject", "retcode"):
+        assert np.array_equal(g[k], r[k]), f"{what}: {k} differs"
+    gu, ru = g["us"], r["us"]
+    if written_only:     # rows a trajectory never reaches are uninitialised on the device
+        t0 = r["ts"][:, :1] * 0 + g["ts"][:, :1] * 0
+        w = np.ones(g["ts"].shape, bool)
+        w[:, 1:] = g["ts"][:, 1:] != g["_t0"]
+        gu, ru = gu[w], ru[w]
+    assert np.array_equal(gu, ru, equal_nan=True), f"{what}: us differs (max |d| = {np.nanmax(np.abs(gu.astype(f64) - ru.astype(f64)))})"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "vern9"])
+def test_gpu_events_decay_bit_exact(oracle, alg):
+    import diffeqgpu_b200 as dg
+    n = 257
+    u0 = (10.0 + np.arange(n)[:, None] * 0.01).astype(f32)
+    p = np.ones((n, 1), f32)
+    cbs = [KICK, KICK4]
+    for kw in (dict(dt=1.0, tstops=[2.4, 4.0]), dict(dt=0.01, tstops=[4.0]), dict(dt=0.5, tstops=[2.4, 4.0], save_everystep=False),
+               dict(dt=1.0, tstops=[2.4, 4.0], saveat=np.array([0.0, 2.4, 6.0, 10.0], f32))):
+        g = gpu_events(dg, "decay", alg, u0, p, [0, 10], cbs, **kw)
+        okw = dict(kw)
+        if "saveat" not in kw and kw.get("save_everystep", True):
+            okw["length"] = g["us"].shape[1]
+        r = oracle.solve("decay", alg, u0, p, [0, 10], callbacks=cbs, **okw)
+        assert_same(g, r, f"fixed {alg} {sorted(kw)}")
+    akw = dict(dt=1.0, adaptive=True, abstol=1e-7, reltol=1e-7)
+    sv = np.arange(0, 11, dtype=f32)
+    for kw in (dict(save_everystep=False, tstops=[4.0]), dict(saveat=sv, tstops=[2.4, 4.0]), dict(saveat=sv)):
+        g = gpu_events(dg, "decay", alg, u0, p, [0, 10], cbs, **akw, **kw)
+        r = oracle.solve("decay", alg, u0, p, [0, 10], callbacks=cbs, **akw, **kw)
+        assert_same(g, r, f"adaptive {alg} {sorted(kw)}")
+    # terminate!: retcode Terminated, later rows keep t0
+    term = [(("u_lt", 0, 1.0), ("terminate", 0, 0.0))]
+    g = gpu_events(dg, "decay", alg, u0, p, [0, 10], term, saveat=sv, **akw)
+    r = oracle.solve("decay", alg, u0, p, [0, 10], callbacks=term, saveat=sv, **akw)
+    g["_t0"] = 0.0
+    assert (g["retcode"] == 6).all() and (g["ts"][:, 4:] == 0).all()
+    assert_same(g, r, f"terminate {alg}", written_only=True)
+
+
+@pytest.mark.gpu
+def test_gpu_events_lorenz_sweep_and_f64(oracle):
+    """tstops without callbacks, a state-dependent callback on a parameter sweep, Float64"""
+    import diffeqgpu_b200 as dg
+    p = lorenz_sweep(1000, seed=21)
+    sv = np.arange(0, 6, dtype=f32)
+    akw = dict(dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, saveat=sv)
+    g = gpu_events(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 5], [], tstops=[0.5, 2.25, 4.0], **akw)
+    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 5], tstops=[0.5, 2.25, 4.0], **akw)
+    assert_same(g, r, "lorenz tstops only")
+    cbs = [(("u_gt", 2, 30.0), ("u_scale", 2, 0.5)), (("t_ge", 0, 4.0), ("p_set", 1, 20.0))]
+    g = gpu_events(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 5], cbs, **akw)
+    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 5], callbacks=cbs, **akw)
+    assert_same(g, r, "lorenz state callbacks")
+    g = gpu_events(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 5], cbs, dt=0.01, tstops=[1.005])
+    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 5], callbacks=cbs, dt=0.01, tstops=[1.005], length=g["us"].shape[1])
+    assert_same(g, r, "lorenz fixed dt callbacks")
+    # Float64 (device pow vs libm pow differ in the last ulp): identical step counts on >= 99 %, and
+    # 10 * reltol on the non-chaotic part of the sweep, with a kick that fires exactly at a tstop
+    p64 = lorenz_sweep(500, f64, seed=22)
+    cb64 = [(("t_eq", 0, 1.5), ("u_scale", 2, 0.5))]
+    kw64 = dict(dt=0.1, adaptive=True, abstol=1e-10, reltol=1e-10, saveat=np.arange(0, 4, dtype=f64), tstops=[1.5])
+    g = gpu_events(dg, "lorenz", "vern9", U0_LORENZ, p64, [0, 3], cb64, dtype=f64, **kw64)
+    r = oracle.solve("lorenz", "vern9", U0_LORENZ, p64, [0, 3], callbacks=cb64, dtype=f64, **kw64)
+    assert (g["naccept"] == r["naccept"]).mean() >= 0.99 and np.array_equal(g["ts"], r["ts"])
+    calm = p64[:, 1] < 13.0
+    rel = np.abs(g["us"] - r["us"]) / np.maximum(np.abs(r["us"]), 1.0)
+    assert rel[calm].max() < 10 * 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_events_need_an_events_program():
+    """tstops through the C ABI on a program built without events is refused, not ignored"""
+    import torch
+    import diffeqgpu_b200 as dg
+    from diffeqgpu_b200 import _lib
+    prob = dg.ODEProblem(dg.models.lorenz, U0_LORENZ.astype(f32), (0.0, 1.0), P0_LORENZ.astype(f32))
+    prog = dg.get_program(prob, dg.GPUTsit5(), "strict", torch.device("cuda:0"))
+    probs = dg.ProblemBatch.from_arrays(prob, p=lorenz_sweep(8), device="cuda:0")
+    ts = torch.empty((8, 2), device="cuda:0"); us = torch.empty((8, 2, 3), device="cuda:0")
+    tst = torch.tensor([0.5], device="cuda:0")
+    a = _lib.SolveArgs()
+    a.n_traj = 8; a.u0 = probs.u0.data_ptr(); a.p = probs.p.data_ptr(); a.p_stride = 3
+    a.tspan = probs.tspan.data_ptr(); a.dt = 0.1; a.n_rows = 2; a.us = us.data_ptr(); a.ts = ts.data_ptr()
+    a.tstops = tst.data_ptr(); a.n_tstops = 1
+    with pytest.raises(dg.DegkError, match="events"):
+        prog.solve(a, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "vern9"])
+def test_gpu_high_level_solve_with_callbacks(alg):
+    """test/gpu_kernel_de/gpu_ode_discrete_callbacks.jl:26-60, 136-160 through solve(EnsembleProblem, ...)
+    (the exact solution stands in for the OrdinaryDiffEq Vern9 benchmark solution)"""
+    import diffeqgpu_b200 as dg
+    prob = dg.ODEProblem(dg.models.decay, np.array([10.0], f32), (0.0, 10.0), np.array([1.0], f32))
+    monteprob = dg.EnsembleProblem(prob, safetycopy=False)
+    cb = dg.DiscreteCallback(*callback_sources(KICK))
+    a = getattr(dg, ALGS[alg])()
+    sol = dg.solve(monteprob, a, dg.EnsembleGPUKernel(), trajectories=2, adaptive=False, dt=f32(1.0), callback=cb,
+                   merge_callbacks=True, tstops=[2.4])
+    s = sol[0]
+    assert s.retcode == "Success" and len(s.t) == 12 and s.t[3] == f32(2.4)
+    exact = np.array([exact_decay_with_kicks(t, [2.4]) for t in s.t]); exact[3] = 10 * math.exp(-2.4)
+    assert np.linalg.norm(s.u[:, 0] - exact) < (5e-3 if alg != "tsit5" else 6e-2)
+    sol = dg.solve(monteprob, a, dg.EnsembleGPUKernel(), trajectories=2, adaptive=True, dt=f32(1.0), abstol=f32(1e-7),
+                   reltol=f32(1e-7), callback=dg.DiscreteCallback(*callback_sources(KICK4)), merge_callbacks=True,
+                   tstops=[4.0], save_everystep=False)
+    assert abs(sol[1].u[-1, 0] - exact_decay_with_kicks(10.0, [4.0])) < 2e-5 and sol[1].t[-1] == f32(10.0)
+    # terminate!: ReturnCode.Terminated with the solution cut at the last written row (src/solve.jl:260-277)
+    term = dg.DiscreteCallback(*callback_sources((("u_lt", 0, 1.0), ("terminate", 0, 0.0))))
+    sol = dg.solve(monteprob, a, dg.EnsembleGPUKernel(), trajectories=2, adaptive=True, dt=f32(0.1), abstol=f32(1e-7),
+                   reltol=f32(1e-7), callback=term, saveat=np.arange(0, 11, dtype=f32))
+    assert sol[0].retcode == "Terminated" and len(sol[0].t) == 3
