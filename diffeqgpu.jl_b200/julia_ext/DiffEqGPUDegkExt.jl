@@ -22,6 +22,8 @@ struct ModelDesc
     builtin::Cstring; rhs_src::Cstring; jac_src::Cstring; tgrad_src::Cstring; noise_src::Cstring
     n_state::Int32; n_param::Int32; n_noise::Int32; noise_kind::Int32
     dtype::Int32; alg::Int32; fp_mode::Int32; force_jit::Int32
+    events::Int32; n_callbacks::Int32                 # tstops / GPUDiscreteCallback lowering (degk.h)
+    cb_condition_src::Ptr{Cstring}; cb_affect_src::Ptr{Cstring}
 end
 
 struct SolveArgs
@@ -37,6 +39,8 @@ struct SolveArgs
     retcode::CuPtr{Int32}; naccept::CuPtr{Int32}; nreject::CuPtr{Int32}
     seed::UInt64; reduce::CuPtr{Float64}; totals::CuPtr{UInt64}
     max_iters::Int64; engine::Int32; reserved::Int32
+    tstops::CuPtr{Cvoid}; n_tstops::Int32; reserved2::Int32
+    nsaved::CuPtr{Int32}
 end
 
 alg_id(::GPUTsit5) = 0; alg_id(::GPUVern7) = 1; alg_id(::GPUVern9) = 2
