@@ -33,7 +33,8 @@ template <class T, class M> using Rodas5PM = Rodas<T, M, true>;
 
 template <int FPMODE, class T, class Model, template <class, class> class Method>
 __global__ void __launch_bounds__(DEGK_BLOCK) k_ode_solve(const KArgs a) {
-    ode_solve_body<T, Model, Method<T, Model>>(a);
+    extern __shared__ __align__(16) unsigned char degk_smem[];
+    ode_solve_body<T, Model, Method<T, Model>>(a, degk_smem);
 }
 template <int FPMODE, class T, class Model, template <class, class> class Method>
 __global__ void __launch_bounds__(DEGK_BLOCK) k_ode_asolve(const KArgs a) {

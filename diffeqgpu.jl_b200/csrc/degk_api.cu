@@ -400,6 +400,20 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
         const int nsv = (a->saveat && a->n_saveat <= 1024) ? a->n_saveat : 0;
         smem = degk_smem2_bytes(prog, nsv);
     }
+    // fixed-dt kernel, every-step saves in the reference layout: stage R rows per lane in shared
+    // memory (<= 48 KB per block, so no opt-in attribute is needed) and flush them coalesced
+    if (which == 0 && !prog->is_sde && !prog->has_events && !a->saveat && a->save_everystep &&
+        a->out_layout == DEGK_LAYOUT_REF && !getenv("DEGK_NO_STAGED_SAVES")) {
+        const size_t es = dtype_size(prog->info.dtype);
+        const int n = prog->info.n_state;
+        const int words_per_lane = (int)(48 * 1024 / (DEGK_BLOCK * es));
+        int R = (words_per_lane - 2) / (n + 1);
+        if (R > 16) R = 16;
+        if (R >= 4) {
+            k.stage_rows = R;
+            smem = (size_t)DEGK_BLOCK * ((size_t)n * R + 1 + R + 1) * es;
+        }
+    }
     long long blocks = (a->n_traj + per_block - 1) / per_block;
     if (sched == DEGK_SCHED_QUEUE) {
         long long resident = (long long)ctx->sm_count * std::max(1, v2 ? prog->info.max_blocks_per_sm2 : prog->info.max_blocks_per_sm);

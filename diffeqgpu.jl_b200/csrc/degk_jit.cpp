@@ -277,7 +277,8 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
         src += std::string("typedef ") + method_type(d->alg) + " METHOD;\n";
         src += std::string("template <class T_, class M_> using METHODT = ") + method_template(d->alg) + ";\n";
         src += "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
-               "    degk::ode_solve_body<REAL, MODEL, METHOD>(a);\n}\n";   // (the first-generation adaptive kernel exists ahead of time only, for A/B runs)
+               "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
+               "    degk::ode_solve_body<REAL, MODEL, METHOD>(a, degk_smem);\n}\n";   // (the first-generation adaptive kernel exists ahead of time only, for A/B runs)
         snprintf(buf, sizeof buf,
                  "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
                  "extern \"C\" __global__ void __launch_bounds__(%d, (sizeof(REAL) == 4 ? 4 : 1)) degk_jit_adaptive2(const degk::KArgs a) {\n"

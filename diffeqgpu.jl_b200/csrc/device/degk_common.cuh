@@ -56,7 +56,8 @@ struct KArgs {
     int reserved;
     int* nsaved;         // optional, per trajectory (saveat runs of the adaptive kernels): rows written
     const void* tstops;  // event-capable kernels (degk_ode_events.cuh): times the steppers must hit
-    int n_tstops; int reserved2;
+    int n_tstops;
+    int stage_rows;      // fixed-dt kernel: rows staged in shared memory per lane before a coalesced flush (0 = off)
 };
 
 // ---- fused multiply-add that stays fused in both fp modes (reference: @muladd / muladd) ----

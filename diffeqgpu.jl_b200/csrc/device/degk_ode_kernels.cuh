@@ -28,24 +28,61 @@ namespace degk {
 // =====================================================================================
 // fixed time step
 // =====================================================================================
+// Every-step saves in the reference layout are 12-byte stores at a stride of len*n*sizeof(T)
+// bytes across the lanes of a warp: 32 sectors per store instruction.  With a.stage_rows = R > 0
+// (host: REF layout, save_everystep, no saveat) each lane buffers R rows of (u, t) in shared
+// memory and the warp then writes every trajectory's R*n contiguous values with consecutive
+// lanes: the same number of store instructions, one eighth of the sectors.
 template <class T, class Model, class Method>
-DEGK_DEV void ode_solve_body(const KArgs& a) {
+DEGK_DEV void ode_solve_body(const KArgs& a, unsigned char* smem_raw) {
     constexpr int N = Model::N;
     const i64 traj = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = traj < a.n_traj;
+    const u32 lane = lane_id();
     u32 nsteps = 0, nfail = 0;
-    if (traj < a.n_traj) {
-        T u[N], uprev[N], unew[N], err[N];
-        T p[Model::NP > 0 ? Model::NP : 1];
-        T t0, tf;
+    T u[N], uprev[N], unew[N], err[N];
+    T p[Model::NP > 0 ? Model::NP : 1];
+    T t0 = (T)0, tf = (T)0;
+    const T dt = (T)a.dt;
+    const T* saveat = (const T*)a.saveat;
+    const bool has_saveat = saveat != nullptr;
+    typename Method::Keep K;
+    int cur = 0;                 // 1-based index of the next saveat entry
+    i64 step_idx = 1;            // 0-based row of the next every-step save
+    i64 ts_written = 0;          // rows [0, ts_written) of ts hold real values
+    T t = (T)0, tprev = (T)0;
+    int rc = RC_SUCCESS;
+    bool first = true;
+    i64 iters = 0;
+    // staging buffers of this warp: [32 lanes][N*R + 1] state words, then [32 lanes][R + 1] times
+    const int R = a.stage_rows;
+    T* wu = nullptr; T* wt = nullptr;
+    int nbuf = 0; i64 k0 = 0;
+    if (R > 0) {
+        const size_t per_warp = (size_t)32 * ((size_t)N * R + 1 + R + 1);
+        wu = (T*)smem_raw + (size_t)(threadIdx.x >> 5) * per_warp;
+        wt = wu + (size_t)32 * ((size_t)N * R + 1);
+    }
+    auto flush = [&]() {         // warp-cooperative: every lane of the warp calls it
+        __syncwarp();
+        for (int j = 0; j < 32; ++j) {
+            const int n = __shfl_sync(0xffffffffu, nbuf, j);
+            if (n == 0) continue;
+            const i64 tr = __shfl_sync(0xffffffffu, traj, j);
+            const i64 kk = __shfl_sync(0xffffffffu, k0, j);
+            i64 nn = a.n_rows - kk;          // rows past len are dropped (the reference would write out of bounds)
+            nn = nn < 0 ? 0 : (nn < n ? nn : n);
+            const T* ub = wu + (size_t)j * ((size_t)N * R + 1);
+            T* ud = (T*)a.us + (tr * a.n_rows + kk) * N;
+            for (int w = (int)lane; w < (int)nn * N; w += 32) ud[w] = ub[w];
+            if (a.ts != nullptr && (i64)lane < nn) ((T*)a.ts)[tr * a.n_rows + kk + lane] = wt[(size_t)j * (R + 1) + lane];
+        }
+        nbuf = 0;
+        __syncwarp();
+    };
+    if (valid) {
         load_problem<T, Model>(a, traj, u, p, t0, tf);
-        const T dt = (T)a.dt;
-        const T* saveat = (const T*)a.saveat;
-        const bool has_saveat = saveat != nullptr;
-        typename Method::Keep K;
         // kernels.jl:34-47
-        int cur = 0;                 // 1-based index of the next saveat entry
-        i64 step_idx = 1;            // 0-based row of the next every-step save
-        i64 ts_written = 0;          // rows [0, ts_written) of ts hold real values
         if (has_saveat) {
             cur = 1;
             if (t0 == saveat[0]) { cur = 2; store_u<T, N>(a, traj, 0, u); store_t<T>(a, traj, 0, t0); }
@@ -55,43 +92,57 @@ DEGK_DEV void ode_solve_body(const KArgs& a) {
             ts_written = 1;
         }
         Method::init(K, u, p, t0);
-        T t = t0, tprev = t0;
-        int rc = RC_SUCCESS;
-        bool first = true;
-        i64 iters = 0;
-        while (t < tf) {
+        t = t0; tprev = t0;
+    }
+    bool active = valid && (t < tf);
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) {
             if (!first) Method::accepted(K);     // FSAL shift deferred so the last step's
             first = false;                       // stages survive for the final interpolation
             DEGK_UNROLL for (int c = 0; c < N; ++c) uprev[c] = u[c];
             tprev = t;
             t = t + dt;                          // integ.t += dt precedes the stages
             if (!Method::template attempt<false>(K, uprev, p, tprev, dt, unew, err)) {
-                rc = RC_SINGULAR; ++nfail; break;
-            }
-            Method::on_accept(K);
-            DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = unew[c];
-            ++nsteps;
-            if (!has_saveat) {
-                if (a.save_everystep) {          // integrator_utils.jl:28-33
-                    store_u<T, N>(a, traj, step_idx, u);
-                    store_t<T>(a, traj, step_idx, t);
-                    ++step_idx;
-                    ts_written = step_idx;
+                rc = RC_SINGULAR; ++nfail; active = false;
+            } else {
+                Method::on_accept(K);
+                DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = unew[c];
+                ++nsteps;
+                if (!has_saveat) {
+                    if (a.save_everystep) {          // integrator_utils.jl:28-33
+                        if (R > 0) {
+                            if (nbuf == 0) k0 = step_idx;
+                            T* ub = wu + (size_t)lane * ((size_t)N * R + 1) + (size_t)nbuf * N;
+                            DEGK_UNROLL for (int c = 0; c < N; ++c) ub[c] = u[c];
+                            wt[(size_t)lane * (R + 1) + nbuf] = t;
+                            ++nbuf;
+                        } else {
+                            store_u<T, N>(a, traj, step_idx, u);
+                            store_t<T>(a, traj, step_idx, t);
+                        }
+                        ++step_idx;
+                        ts_written = step_idx;
+                    }
+                } else {                             // integrator_utils.jl:34-47
+                    while (cur <= a.n_saveat && saveat[cur - 1] <= t) {
+                        const T savet = saveat[cur - 1];
+                        const T theta = (savet - tprev) / dt;
+                        T v[N];
+                        Method::interp(K, theta, dt, uprev, u, p, tprev, v);
+                        store_u<T, N>(a, traj, cur - 1, v);
+                        store_t<T>(a, traj, cur - 1, savet);
+                        ts_written = cur;
+                        ++cur;
+                    }
                 }
-            } else {                             // integrator_utils.jl:34-47
-                while (cur <= a.n_saveat && saveat[cur - 1] <= t) {
-                    const T savet = saveat[cur - 1];
-                    const T theta = (savet - tprev) / dt;
-                    T v[N];
-                    Method::interp(K, theta, dt, uprev, u, p, tprev, v);
-                    store_u<T, N>(a, traj, cur - 1, v);
-                    store_t<T>(a, traj, cur - 1, savet);
-                    ts_written = cur;
-                    ++cur;
-                }
+                if (++iters >= a.max_iters) { rc = RC_MAXITERS; ++nfail; active = false; }
+                else active = t < tf;
             }
-            if (++iters >= a.max_iters) { rc = RC_MAXITERS; ++nfail; break; }
         }
+        if (R > 0 && __any_sync(0xffffffffu, nbuf >= R)) flush();
+    }
+    if (R > 0) flush();
+    if (valid) {
         if (rc == RC_SUCCESS) {
             if (t > tf && !has_saveat) {         // kernels.jl:53-57
                 const T theta = (tf - tprev) / dt;
