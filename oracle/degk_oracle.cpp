@@ -703,7 +703,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
 #endif
     std::vector<T> tstops_T(a.n_tstops);
     for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
-    if ((a.n_tstops > 0 || a.n_cb > 0) && !tab) return -3;   // events: explicit RK steppers only
+    if ((a.n_tstops > 0 || a.n_cb > 0) && (a.alg == A_EM || a.alg == A_SIEA)) return -3;   // events: ODE steppers only
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < a.n_traj; ++i) {
         const T* ui = u0 + i * a.u0_stride;
@@ -734,6 +734,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
             I.u_modified = true; I.naccept = I.nreject = I.nf = 0; I.retcode = RC_DEFAULT;
             T two = (T)2;
             I.d = (T)1 / (two + std::sqrt(two));    // stiff/types.jl:47-48
+            I.tstops = tstops_T.empty() ? nullptr : tstops_T.data(); I.n_tstops = (int)tstops_T.size(); I.tstops_idx = 0;
             drive<T>(I, a, order, t0, tf, ui, out, saveat);
             na = I.naccept; nr = I.nreject; rc = I.retcode;
         } else {

@@ -120,9 +120,11 @@ def test_callback_bodies_compile_with_nvrtc():
     # tstops without callbacks: events flag only
     st, nbytes, log = _lib.jit_compile_check(_lib.make_desc(builtin="lorenz", dtype=_lib.F32, alg=0, events=True))
     assert st == 0, log
-    # stiff solvers: not lowered
-    st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="rober", dtype=_lib.F32, alg=5, events=True))
-    assert st != 0 and "explicit RK" in log
+    # Rosenbrock steppers take the same hooks (stiff_ode/gpu_ode_discrete_callbacks.jl); SDE solvers do not
+    st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="rober", dtype=_lib.F32, alg=5, callbacks=[callback_sources(KICK)]))
+    assert st == 0, log
+    st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="gbm", dtype=_lib.F32, alg=6, events=True, noise_kind=_lib.NOISE_DIAGONAL))
+    assert st != 0 and "ODE solvers only" in log
     # a broken body reports the NVRTC log
     st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="decay", dtype=_lib.F32, alg=0,
                                                        callbacks=[("return t == ;", "u[0] = 1;")]))
@@ -143,7 +145,8 @@ def test_callback_argument_checks():
 # ------------------------------------------------------------------------------------------
 # GPU: the event kernels against the oracle, bit for bit in strict mode
 # ------------------------------------------------------------------------------------------
-ALGS = {"tsit5": "GPUTsit5", "vern7": "GPUVern7", "vern9": "GPUVern9"}
+ALGS = {"tsit5": "GPUTsit5", "vern7": "GPUVern7", "vern9": "GPUVern9", "rosenbrock23": "GPURosenbrock23",
+        "rodas4": "GPURodas4", "rodas5p": "GPURodas5P"}
 
 
 def gpu_events(dg, model, alg, u0, p, tspan, specs, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3, saveat=None,
@@ -286,3 +289,47 @@ def test_gpu_high_level_solve_with_callbacks(alg):
     sol = dg.solve(monteprob, a, dg.EnsembleGPUKernel(), trajectories=2, adaptive=True, dt=f32(0.1), abstol=f32(1e-7),
                    reltol=f32(1e-7), callback=term, saveat=np.arange(0, 11, dtype=f32))
     assert sol[0].retcode == "Terminated" and len(sol[0].t) == 3
+
+
+@pytest.mark.parametrize("alg", ["rosenbrock23", "rodas4", "rodas5p"])
+def test_oracle_stiff_events(oracle, alg):
+    """test/gpu_kernel_de/stiff_ode/gpu_ode_discrete_callbacks.jl: same checks for the Rosenbrock steppers"""
+    tol = 5e-5 if alg != "rosenbrock23" else 5e-4
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.1, adaptive=True, abstol=1e-7, reltol=1e-7,
+                     save_everystep=False, tstops=[4.0], callbacks=[KICK4])
+    assert r["ts"][0, 1] == f32(10.0) and abs(r["us"][0, 1, 0] - exact_decay_with_kicks(10.0, [4.0])) < tol
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.5, length=22, tstops=[2.4], callbacks=[KICK])
+    assert np.allclose(r["ts"][0][:7], [0, 0.5, 1, 1.5, 2, 2.4, 2.9], atol=1e-6)
+    assert abs(r["us"][0, -1, 0] - exact_decay_with_kicks(10.0, [2.4])) < (5e-4 if alg == "rosenbrock23" else 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["rosenbrock23", "rodas4", "rodas5p"])
+def test_gpu_stiff_events_bit_exact(oracle, alg):
+    import diffeqgpu_b200 as dg
+    n = 130
+    u0 = (10.0 + np.arange(n)[:, None] * 0.01).astype(f32)
+    p = np.ones((n, 1), f32)
+    cbs = [KICK, KICK4]
+    sv = np.arange(0, 11, dtype=f32)
+    for kw in (dict(dt=0.5, tstops=[2.4, 4.0]), dict(dt=0.25, tstops=[2.4], saveat=np.array([0.0, 2.4, 6.0, 10.0], f32))):
+        g = gpu_events(dg, "decay", alg, u0, p, [0, 10], cbs, **kw)
+        okw = dict(kw)
+        if "saveat" not in kw:
+            okw["length"] = g["us"].shape[1]
+        r = oracle.solve("decay", alg, u0, p, [0, 10], callbacks=cbs, **okw)
+        assert_same(g, r, f"stiff fixed {alg} {sorted(kw)}")
+    akw = dict(dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6)
+    for kw in (dict(save_everystep=False, tstops=[4.0]), dict(saveat=sv, tstops=[2.4, 4.0])):
+        g = gpu_events(dg, "decay", alg, u0, p, [0, 10], cbs, **akw, **kw)
+        r = oracle.solve("decay", alg, u0, p, [0, 10], callbacks=cbs, **akw, **kw)
+        assert_same(g, r, f"stiff adaptive {alg} {sorted(kw)}")
+    # Robertson sweep with a terminate! once y3 > 0.5
+    k = (np.array([0.04, 3e7, 1e4]) * (0.5 + np.random.default_rng(3).random((64, 3)))).astype(f32)
+    term = [(("u_gt", 2, 0.5), ("terminate", 0, 0.0))]
+    rkw = dict(dt=1e-4, adaptive=True, abstol=1e-8, reltol=1e-4, saveat=np.array([1.0, 10.0, 100.0, 1e3, 1e4, 1e5], f32))
+    g = gpu_events(dg, "rober", alg, [1, 0, 0], k, [0, 1e5], term, **rkw)
+    r = oracle.solve("rober", alg, [1, 0, 0], k, [0, 1e5], callbacks=term, **rkw)
+    g["_t0"] = 0.0
+    assert (g["retcode"] == 6).any()
+    assert_same(g, r, f"rober terminate {alg}", written_only=True)
