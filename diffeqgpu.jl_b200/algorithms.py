@@ -31,9 +31,9 @@ class GPUSDEAlgorithm(GPUODEAlgorithm):
 
 
 class GPUODEImplicitAlgorithm(GPUODEAlgorithm):
-    """reference: GPUODEImplicitAlgorithm{AD}; only the analytic-Jacobian branch of
-    nlsolve/type.jl:129-140 is lowered here, so `autodiff` is accepted but a Jacobian body
-    (or a built-in model that has one) is required."""
+    """reference: GPUODEImplicitAlgorithm{AD}.  Jacobian / time gradient as in nlsolve/type.jl:129-157:
+    the function's own `jac` when it has one, else forward-mode duals (autodiff = True, the
+    default) or finite differences (autodiff = False)."""
     is_stiff = True
 
     def __init__(self, autodiff=True):

@@ -196,20 +196,20 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
             degk_set_error(ctx, "n_state must be in 1..64 and n_param, n_noise >= 0");
             return DEGK_ERR_INVALID;
         }
-        if (stiff && !d->jac_src) {
-            // reference: nlsolve/type.jl:131-137 falls back to ForwardDiff / finite differences;
-            // that lowering is not available here
-            degk_set_error(ctx, "the stiff solvers need an analytic Jacobian body (jac_src)");
-            return DEGK_ERR_UNSUPPORTED;
-        }
+        if (d->jac_mode < 0 || d->jac_mode > 2) { degk_set_error(ctx, "jac_mode must be 0, 1 or 2"); return DEGK_ERR_INVALID; }
         if (is_sde && !d->noise_src) { degk_set_error(ctx, "SDE solvers need noise_src"); return DEGK_ERR_INVALID; }
         const int noise = is_sde ? d->noise_kind : 0;
         const int m = noise == DEGK_NOISE_GENERAL ? d->n_noise : d->n_state;
         src += "namespace degk {\nstruct UserModel {\n";
+        // no jac body: nlsolve/type.jl:131-137 -- ForwardDiff (jac_mode 0/2, the reference default
+        // autodiff = true) or finite differences (jac_mode 1); see degk_dual.cuh
+        const bool has_tgrad = d->jac_src || d->tgrad_src;
         snprintf(buf, sizeof buf,
                  "    static constexpr int N = %d, NP = %d, M = %d, NOISE = %d;\n"
-                 "    static constexpr bool HAS_JAC = %s, HAS_TGRAD = %s;\n",
-                 d->n_state, d->n_param, m, noise, d->jac_src ? "true" : "false", d->jac_src ? "true" : "false");
+                 "    static constexpr bool HAS_JAC = %s, HAS_TGRAD = %s;\n"
+                 "    static constexpr int JAC_MODE = %d;\n",
+                 d->n_state, d->n_param, m, noise, d->jac_src ? "true" : "false", has_tgrad ? "true" : "false",
+                 d->jac_mode == 1 ? 1 : 2);
         src += buf;
         src += "    template <class T> static DEGK_DEV void f(T (&du)[N], const T (&u)[N], const T* p, T t) {\n";
         src += d->rhs_src;
@@ -219,6 +219,8 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                    "        DEGK_UNROLL for (int i_ = 0; i_ < N; ++i_) DEGK_UNROLL for (int j_ = 0; j_ < N; ++j_) J[i_][j_] = (T)0;\n";
             src += d->jac_src;
             src += "\n    }\n";
+        }
+        if (has_tgrad) {
             src += "    template <class T> static DEGK_DEV void tgrad(T (&dT)[N], const T (&u)[N], const T* p, T t) {\n"
                    "        DEGK_UNROLL for (int i_ = 0; i_ < N; ++i_) dT[i_] = (T)0;\n";
             if (d->tgrad_src) src += d->tgrad_src;
@@ -239,7 +241,17 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
         const char* st = d->builtin ? builtin_struct(d->builtin) : nullptr;
         if (!st) { degk_set_error(ctx, "unknown built-in model '%s'", d->builtin ? d->builtin : "(null)"); return DEGK_ERR_INVALID; }
         src += "#include \"degk_models.cuh\"\n";
-        src += std::string("typedef degk::") + st + " MODEL;\n";
+        if (d->jac_mode != 0 && stiff) {
+            // a built-in model asked to ignore its analytic Jacobian (jac_mode 1: finite differences,
+            // 2: forward-mode duals) -- used to validate those paths against the analytic one
+            snprintf(buf, sizeof buf,
+                     "namespace degk { struct ModelNoJac : %s {\n"
+                     "    static constexpr bool HAS_JAC = false, HAS_TGRAD = false;\n"
+                     "    static constexpr int JAC_MODE = %d;\n}; }\ntypedef degk::ModelNoJac MODEL;\n", st, d->jac_mode);
+            src += buf;
+        } else {
+            src += std::string("typedef degk::") + st + " MODEL;\n";
+        }
     }
     snprintf(buf, sizeof buf, "#define DEGK_JIT_BLOCK %d\n", DEGK_BLOCK);
     src += buf;

@@ -14,6 +14,7 @@
 #pragma once
 #include "degk_common.cuh"
 #include "degk_pack.cuh"
+#include "degk_dual.cuh"
 #include "gen_rodas_consts.cuh"
 
 namespace degk {
@@ -150,14 +151,13 @@ struct Rosenbrock23 {
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
                                  T (&unew)[N], T (&err)[N]) {
-        static_assert(Model::HAS_JAC && Model::HAS_TGRAD, "stiff solvers need analytic jac/tgrad");
         const T two = (T)2;
         const T d = (T)1 / (two + sqrt_(two));            // stiff/types.jl:47-48
         const T gam = h * d;
         const T dto2 = h / (T)2, dto6 = h / (T)6;
         T J[N][N], W[N][N], dT[N];
-        Model::template jac<T>(J, uprev, p, t);
-        Model::template tgrad<T>(dT, uprev, p, t);
+        eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
+        eval_tgrad<T, Model>(dT, uprev, p, t);
         DEGK_UNROLL for (int i = 0; i < N; ++i)
             DEGK_UNROLL for (int j = 0; j < N; ++j) {
                 const T v = -(gam * J[i][j]);
@@ -225,10 +225,9 @@ struct Rodas {
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
                                  T (&unew)[N], T (&err)[N]) {
-        static_assert(Model::HAS_JAC && Model::HAS_TGRAD, "stiff solvers need analytic jac/tgrad");
         T J[N][N], dT[N];
-        Model::template jac<T>(J, uprev, p, t);
-        Model::template tgrad<T>(dT, uprev, p, t);
+        eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
+        eval_tgrad<T, Model>(dT, uprev, p, t);
         const T dtgamma = h * RC(gamma);
         const T invdg = (T)1 / dtgamma;
         DEGK_UNROLL for (int i = 0; i < N; ++i) J[i][i] = J[i][i] - invdg;    // W = J - I/(dt*gamma)

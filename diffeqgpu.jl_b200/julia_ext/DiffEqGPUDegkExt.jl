@@ -24,6 +24,7 @@ struct ModelDesc
     dtype::Int32; alg::Int32; fp_mode::Int32; force_jit::Int32
     events::Int32; n_callbacks::Int32                 # tstops / GPUDiscreteCallback lowering (degk.h)
     cb_condition_src::Ptr{Cstring}; cb_affect_src::Ptr{Cstring}
+    jac_mode::Int32; reserved::Int32                  # 0 analytic/default, 1 finite differences, 2 ForwardDiff-style duals
 end
 
 struct SolveArgs

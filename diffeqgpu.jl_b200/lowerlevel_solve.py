@@ -78,7 +78,18 @@ def _convert_saveat_adaptive(saveat, prob):
 
 
 def _model_key(f):
-    return (f.builtin, f.rhs, f.jac, f.tgrad, f.n_state, f.n_param, f.force_jit)
+    return (f.builtin, f.rhs, f.jac, f.tgrad, f.n_state, f.n_param, f.force_jit, f.use_jac)
+
+
+def _jac_mode(f, alg):
+    """nlsolve/type.jl:129-137: f.jac if the function has one, else ForwardDiff when the algorithm's
+    autodiff flag is set (the default), else finite differences."""
+    if not getattr(alg, "is_stiff", False):
+        return 0, f.jac
+    has_jac = f.use_jac and (f.jac is not None or (f.builtin is not None and f.rhs is None))
+    if has_jac:
+        return 0, f.jac
+    return (2 if getattr(alg, "autodiff", True) else 1), None
 
 
 def get_program(prob, alg, fp_mode="strict", device=None, callback=None, events=False):
@@ -99,11 +110,12 @@ def get_program(prob, alg, fp_mode="strict", device=None, callback=None, events=
                               fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit)
     else:
         f = prob.f
-        key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode, events, cbs.key())
-        desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, jac_src=f.jac, tgrad_src=f.tgrad,
+        jac_mode, jac_src = _jac_mode(f, alg)
+        key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode, events, cbs.key(), jac_mode)
+        desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, jac_src=jac_src, tgrad_src=f.tgrad if jac_mode == 0 else None,
                               n_state=f.n_state, n_param=f.n_param, dtype=dtype, alg=alg.alg_id,
                               fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit, events=events,
-                              callbacks=cbs.key())
+                              callbacks=cbs.key(), jac_mode=jac_mode)
     return ctx.program(desc, key)
 
 

@@ -57,6 +57,12 @@ linear15 = ODEFunction(builtin="linear15", force_jit=True, python=lambda u, p, t
 linear15_src = ODEFunction(rhs=LINEAR15_RHS, jac=LINEAR15_JAC, n_state=15, n_param=0,
                            python=lambda u, p, t: 1.01 * np.asarray(u))
 
+# test/gpu_kernel_de/finite_diff.jl:6-9 / forward_diff.jl: du = -p u^2, NO analytic Jacobian: the stiff
+# solvers differentiate it (forward-mode duals, or finite differences with autodiff = False)
+QUAD_DECAY_RHS = "    du[0] = -p[0] * u[0] * u[0];\n"
+quad_decay_src = ODEFunction(rhs=QUAD_DECAY_RHS, n_state=1, n_param=1, python=lambda u, p, t: np.array([-p[0] * u[0] * u[0]]))
+quad_decay_jac_src = ODEFunction(rhs=QUAD_DECAY_RHS, jac="    J[0][0] = (T)-2 * p[0] * u[0];\n", n_state=1, n_param=1)
+
 # SDEs: test/gpu_kernel_de/gpu_sde_regression.jl:8-11 (dX = p1 X dt + p2 X dW), :46-55 (Lorenz +
 # additive noise g = 3), :86-110 (non-diagonal 2x4 noise)
 gbm = SDEFunction(ODEFunction(builtin="gbm"))

@@ -36,6 +36,7 @@ class ODEFunction:
     n_param: int = 0
     python: Optional[Callable] = field(default=None, compare=False)
     force_jit: bool = False
+    use_jac: bool = True      # False: ignore the analytic Jacobian (the function "has no jac"), for the AD / FD paths
 
     def __post_init__(self):
         if self.builtin is None and self.rhs is None:

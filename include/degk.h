@@ -104,7 +104,7 @@ typedef enum { DEGK_NOISE_NONE = 0, DEGK_NOISE_DIAGONAL = 1, DEGK_NOISE_GENERAL 
 typedef struct {
     const char* builtin;    /* or NULL */
     const char* rhs_src;    /* du[...] = f(u, p, t)            (required when builtin == NULL) */
-    const char* jac_src;    /* J[i][j] = d f_i / d u_j         (required by the stiff solvers) */
+    const char* jac_src;    /* J[i][j] = d f_i / d u_j         (optional: see jac_mode) */
     const char* tgrad_src;  /* dT[i] = d f_i / d t             (NULL => zero) */
     const char* noise_src;  /* diagonal: g[i]; general: G[i][j] (SDE only) */
     int32_t n_state, n_param, n_noise;
@@ -124,6 +124,13 @@ typedef struct {
     int32_t n_callbacks;
     const char* const* cb_condition_src;
     const char* const* cb_affect_src;
+    /* Stiff solvers, model without an analytic Jacobian body (reference nlsolve/type.jl:129-157):
+     * 0 = the default: jac_src / the built-in's Jacobian when there is one, else forward-mode duals
+     *     (ForwardDiff.jacobian, alg autodiff = true);
+     * 1 = finite differences (autodiff = false: finite_diff_jac, alg_utils.jl:17-27);
+     * 2 = forward-mode duals.  On a built-in model 1 and 2 ignore its analytic Jacobian. */
+    int32_t jac_mode;
+    int32_t reserved;
 } degk_model_desc;
 
 typedef struct {

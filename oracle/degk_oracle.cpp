@@ -84,7 +84,8 @@ template <class T> inline T thresh(double lit, int via_f32) {
 // Models (restated from the reference's tests / SURVEY §8d)
 // =====================================================================================
 enum ModelId { M_LORENZ = 0, M_HENON_HEILES = 1, M_ROBER = 2, M_DECAY = 3, M_LINEAR15 = 4,
-               M_GBM = 5, M_LORENZ_ADDITIVE = 6, M_SCALAR_SDE = 7, M_OSC_T = 8, M_GBM_ND = 9 };
+               M_GBM = 5, M_LORENZ_ADDITIVE = 6, M_SCALAR_SDE = 7, M_OSC_T = 8, M_GBM_ND = 9,
+               M_QUAD_DECAY = 10 };   // du = -p u^2: test/gpu_kernel_de/finite_diff.jl:6-9, forward_diff.jl
 
 struct ModelInfo { int n, np, m; bool has_jac; bool diag_noise; };
 
@@ -100,9 +101,40 @@ inline ModelInfo model_info(int id) {
     case M_SCALAR_SDE:      return {1, 2, 1, false, true};
     case M_OSC_T:           return {2, 1, 0, true, true};    // non-autonomous forced oscillator
     case M_GBM_ND:          return {2, 2, 4, false, false};  // 2x4 non-diagonal noise
+    case M_QUAD_DECAY:      return {1, 1, 0, true, true};
     }
     return {0, 0, 0, false, true};
 }
+
+// Forward-mode dual numbers for the `ForwardDiff.jacobian` / `ForwardDiff.derivative` branch of
+// nlsolve/type.jl:129-157.  ForwardDiff is not vendored; arithmetic restated from its dual.jl:
+//   x*y: (vx*vy, muladd(vy, px, vx*py))     x/y: (vx/vy, muladd(inv(vy), px, (-(vx/(vy*vy)))*py))
+//   f(x): (f(vx), f'(vx)*px) with DiffRules derivatives.  p and t enter with zero partials.
+template <class T, int NP>
+struct ODual {
+    T v; T d[NP];
+    ODual() {}
+    ODual(T x) : v(x) { for (int i = 0; i < NP; ++i) d[i] = (T)0; }
+    template <class U> ODual(U x) : v((T)x) { for (int i = 0; i < NP; ++i) d[i] = (T)0; }
+    friend ODual operator+(const ODual& a, const ODual& b) { ODual r; r.v = a.v + b.v; for (int i = 0; i < NP; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+    friend ODual operator-(const ODual& a, const ODual& b) { ODual r; r.v = a.v - b.v; for (int i = 0; i < NP; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+    friend ODual operator-(const ODual& a) { ODual r; r.v = -a.v; for (int i = 0; i < NP; ++i) r.d[i] = -a.d[i]; return r; }
+    friend ODual operator*(const ODual& a, const ODual& b) {
+        ODual r; r.v = a.v * b.v;
+        for (int i = 0; i < NP; ++i) r.d[i] = fmaT<T>(b.v, a.d[i], a.v * b.d[i]);
+        return r;
+    }
+    friend ODual operator/(const ODual& a, const ODual& b) {
+        ODual r; r.v = a.v / b.v;
+        const T ib = (T)1 / b.v, c = -(a.v / (b.v * b.v));
+        for (int i = 0; i < NP; ++i) r.d[i] = fmaT<T>(ib, a.d[i], c * b.d[i]);
+        return r;
+    }
+    static ODual chain(T val, T deriv, const ODual& x) { ODual r; r.v = val; for (int i = 0; i < NP; ++i) r.d[i] = deriv * x.d[i]; return r; }
+    friend ODual sin(const ODual& x) { return chain(std::sin(x.v), std::cos(x.v), x); }
+    friend ODual cos(const ODual& x) { return chain(std::cos(x.v), -std::sin(x.v), x); }
+    friend ODual exp(const ODual& x) { const T e = std::exp(x.v); return chain(e, e, x); }
+};
 
 // f(u,p,t).  lorenz: test/gpu_kernel_de/gpu_ode_regression.jl:4-12.
 // rober (ODE form): test/gpu_kernel_de/stiff_ode/gpu_ode_mass_matrix.jl:5-13 with the third
@@ -141,11 +173,14 @@ inline void model_f(int id, T* du, const T* u, const T* p, T t) {
         break;
     case M_OSC_T:          // x'' = -x + p cos(t)
         du[0] = u[1];
-        du[1] = -u[0] + p[0] * std::cos(t);
+        { using std::cos; du[1] = -u[0] + p[0] * cos(t); }
         break;
     case M_GBM_ND:
         du[0] = p[0] * u[0];
         du[1] = p[0] * u[1];
+        break;
+    case M_QUAD_DECAY:
+        du[0] = -p[0] * u[0] * u[0];
         break;
     }
 }
@@ -174,6 +209,9 @@ inline void model_jac(int id, T (*J)[MAXN], const T* u, const T* p, T t) {
         break;
     case M_OSC_T:
         J[0][1] = (T)1; J[1][0] = (T)-1;
+        break;
+    case M_QUAD_DECAY:
+        J[0][0] = (T)-2 * p[0] * u[0];
         break;
     default: break;
     }
@@ -571,6 +609,7 @@ struct SolveArgs {
     // also lower to CUDA-C source for the device (tests/cases.py)
     int n_tstops = 0; const double* tstops = nullptr;
     int n_cb = 0; const int32_t* cb_i = nullptr; const double* cb_v = nullptr;
+    int jac_mode = 0;   // stiff steppers: 0 analytic jac/tgrad, 1 finite differences, 2 forward-mode duals
 };
 
 // condition kinds: 0 t == v | 1 u[i] < v | 2 u[i] > v | 3 t >= v
@@ -734,6 +773,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
             I.u_modified = true; I.naccept = I.nreject = I.nf = 0; I.retcode = RC_DEFAULT;
             T two = (T)2;
             I.d = (T)1 / (two + std::sqrt(two));    // stiff/types.jl:47-48
+            I.jac_mode = a.jac_mode;
             I.tstops = tstops_T.empty() ? nullptr : tstops_T.data(); I.n_tstops = (int)tstops_T.size(); I.tstops_idx = 0;
             drive<T>(I, a, order, t0, tf, ui, out, saveat);
             na = I.naccept; nr = I.nreject; rc = I.retcode;
@@ -787,7 +827,8 @@ int degk_oracle_solve_events(int dtype, int model, int alg, int adaptive, int64_
                              void* us, void* ts, int64_t len,
                              int32_t* naccept, int32_t* nreject, int32_t* retcode,
                              int fma_stages, int nthreads,
-                             const double* tstops, int n_tstops, const int32_t* cb_i, const double* cb_v, int n_cb) {
+                             const double* tstops, int n_tstops, const int32_t* cb_i, const double* cb_v, int n_cb,
+                             int jac_mode) {
     SolveArgs a;
     a.model = model; a.alg = alg; a.adaptive = adaptive; a.save_everystep = save_everystep;
     a.nsave = nsave; a.fma_stages = fma_stages; a.n_traj = n_traj; a.len = len;
@@ -795,6 +836,7 @@ int degk_oracle_solve_events(int dtype, int model, int alg, int adaptive, int64_
     a.dt = dt; a.abstol = abstol; a.reltol = reltol; a.seed = seed;
     a.max_iters = 10000000;
     a.tstops = tstops; a.n_tstops = n_tstops; a.cb_i = cb_i; a.cb_v = cb_v; a.n_cb = n_cb;
+    a.jac_mode = jac_mode;
     if (dtype == 0)
         return solve_T<float>(a, (const float*)u0, (const float*)p, (const float*)tspan,
                               (const float*)saveat, (float*)us, (float*)ts, naccept, nreject,

@@ -14,7 +14,7 @@ _LIB_PATH = _HERE / "_build" / "libdegk_oracle.so"
 _SRCS = ("degk_oracle.cpp", "oracle_stiff.inc", "oracle_sde.inc", "oracle_tables.inc")
 
 MODELS = {"lorenz": 0, "henon_heiles": 1, "rober": 2, "decay": 3, "linear15": 4, "gbm": 5,
-          "lorenz_additive": 6, "scalar_sde": 7, "osc_t": 8, "gbm_nd": 9}
+          "lorenz_additive": 6, "scalar_sde": 7, "osc_t": 8, "gbm_nd": 9, "quad_decay": 10}
 ALGS = {"tsit5": 0, "vern7": 1, "vern9": 2, "rosenbrock23": 3, "rodas4": 4, "rodas5p": 5,
         "em": 6, "siea": 7}
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
@@ -52,7 +52,7 @@ def lib():
             ctypes.c_int, ctypes.c_int]
         _lib.degk_oracle_solve_events.restype = ctypes.c_int
         _lib.degk_oracle_solve_events.argtypes = _lib.degk_oracle_solve.argtypes + [
-            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         _lib.degk_oracle_num_threads.restype = ctypes.c_int
     return _lib
 
@@ -70,7 +70,7 @@ def _ptr(a):
 
 def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3,
           saveat=None, save_everystep=True, length=None, seed=0, dtype=np.float32,
-          fma_stages=False, nthreads=0, tstops=None, callbacks=()):
+          fma_stages=False, nthreads=0, tstops=None, callbacks=(), jac_mode=0):
     """Solve a batch; returns dict(ts=(N,len), us=(N,len,n), naccept, nreject, retcode).
 
     u0: (N,n) or (n,) broadcast; p: (N,np) or (np,) broadcast; tspan: (2,) or (N,2).
@@ -79,6 +79,7 @@ def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1
     tstops: times the steppers must hit; callbacks: sequence of
     ((cond_kind, cond_idx, cond_val), (affect_kind, affect_idx, affect_val)) discrete callbacks
     (kinds: COND_KINDS / AFFECT_KINDS), applied in order after every step.
+    jac_mode (stiff solvers): 0 analytic jac/tgrad, 1 finite differences, 2 forward-mode duals.
     """
     dtype = np.dtype(dtype)
     n, npar, _, _ = model_info(model)
@@ -110,7 +111,7 @@ def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1
             float(dtype.type(dt)), float(dtype.type(abstol)), float(dtype.type(reltol)),
             _ptr(saveat), 0 if saveat is None else len(saveat), int(save_everystep), int(seed),
             _ptr(us), _ptr(ts), length, _ptr(na), _ptr(nr), _ptr(rc), int(fma_stages), int(nthreads)]
-    if tstops is not None or len(callbacks):
+    if tstops is not None or len(callbacks) or jac_mode:
         # tstops reach the integrator already converted to the time type (adapt(backend, tstops))
         tst = np.ascontiguousarray([] if tstops is None else np.asarray(tstops, dtype=dtype), dtype=np.float64)
         cb_i = np.zeros((max(len(callbacks), 1), 4), np.int32)
@@ -118,7 +119,7 @@ def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1
         for c, ((ck, ci, cv), (ak, ai, av)) in enumerate(callbacks):
             cb_i[c] = (COND_KINDS[ck], ci, AFFECT_KINDS[ak], ai)
             cb_v[c] = (float(dtype.type(cv)), float(dtype.type(av)))
-        r = lib().degk_oracle_solve_events(*args, _ptr(tst), len(tst), _ptr(cb_i), _ptr(cb_v), len(callbacks))
+        r = lib().degk_oracle_solve_events(*args, _ptr(tst), len(tst), _ptr(cb_i), _ptr(cb_v), len(callbacks), int(jac_mode))
     else:
         r = lib().degk_oracle_solve(*args)
     if r != 0:

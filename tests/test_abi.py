@@ -99,9 +99,11 @@ def test_nvrtc_reports_errors_not_crashes():
     d = _lib.make_desc(rhs_src="du[0] = undefined_symbol;", n_state=1, alg=0)
     st, nbytes, log = _lib.jit_compile_check(d)
     assert st == _lib.ERR_NVRTC and "undefined_symbol" in log
-    d = _lib.make_desc(rhs_src=dg.models.LORENZ_RHS, n_state=3, n_param=3, alg=5)   # stiff without jac
-    st, _, log = _lib.jit_compile_check(d)
-    assert st == _lib.ERR_UNSUPPORTED and "Jacobian" in log
+    d = _lib.make_desc(rhs_src=dg.models.LORENZ_RHS, n_state=3, n_param=3, alg=5)   # stiff without jac:
+    st, nb, log = _lib.jit_compile_check(d)                                            # forward-mode duals
+    assert st == _lib.OK and nb > 0, log
+    st, _, log = _lib.jit_compile_check(_lib.make_desc(rhs_src=dg.models.LORENZ_RHS, n_state=3, n_param=3, alg=5, jac_mode=7))
+    assert st == _lib.ERR_INVALID and "jac_mode" in log
 
 
 def test_product_does_not_import_oracle():

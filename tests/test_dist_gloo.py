@@ -37,7 +37,15 @@ print("rank", rank, "ok", lo, hi)
 def test_two_rank_sharding_and_moment_allreduce(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    # build the oracle once here: two workers racing `make` on a stale library would both fail
+    sys.path.insert(0, str(ROOT))
+    from oracle import oracle
+    oracle.build()
+    import socket
+    with socket.socket() as sk:                      # a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
     procs = []
     for r in range(2):
         e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
