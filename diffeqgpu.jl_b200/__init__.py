@@ -15,7 +15,7 @@ the repository root:  `import diffeqgpu_b200 as dg`.
 """
 from . import _lib, models
 from ._lib import DegkError
-from .algorithms import (EnsembleGPUKernel, GPUEM, GPUODEAlgorithm, GPUODEImplicitAlgorithm,
+from .algorithms import (EnsembleGPUKernel, GPUEM, GPUKvaerno3, GPUKvaerno5, GPUODEAlgorithm, GPUODEImplicitAlgorithm,
                          GPURodas4, GPURodas5P, GPURosenbrock23, GPUSDEAlgorithm, GPUSIEA,
                          GPUTsit5, GPUVern7, GPUVern9, alg_order)
 from .callbacks import CallbackSet, ContinuousCallback, DiscreteCallback, GPUDiscreteCallback
@@ -31,5 +31,5 @@ __all__ = [
     "vectorized_solve", "EnsembleContext", "EnsembleProblem", "ODEFunction", "ODEProblem",
     "ProblemBatch", "SDEFunction", "SDEProblem", "adapt", "make_prob_compatible", "remake",
     "EnsembleSolution", "ODESolution", "solve", "solve_host", "models",
-    "CallbackSet", "ContinuousCallback", "DiscreteCallback", "GPUDiscreteCallback",
+    "GPUKvaerno3", "GPUKvaerno5", "CallbackSet", "ContinuousCallback", "DiscreteCallback", "GPUDiscreteCallback",
 ]

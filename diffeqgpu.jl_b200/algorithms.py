@@ -64,6 +64,15 @@ class GPURodas5P(GPUODEImplicitAlgorithm):
     alg_id, order = 5, 5
 
 
+class GPUKvaerno3(GPUODEImplicitAlgorithm):
+    """ESDIRK + Newton (gpu_kvaerno3_perform_step.jl); no dense output in the reference: no saveat"""
+    alg_id, order = 8, 3
+
+
+class GPUKvaerno5(GPUODEImplicitAlgorithm):
+    alg_id, order = 9, 5
+
+
 class GPUEM(GPUSDEAlgorithm):
     alg_id, order = 6, 1
 

@@ -16,6 +16,7 @@
 #include "device/gen_erk_vern7.cuh"
 #include "device/gen_erk_vern9.cuh"
 #include "device/degk_rosenbrock.cuh"
+#include "device/degk_kvaerno.cuh"
 #include "device/degk_ode_kernels.cuh"
 #include "device/degk_ode_kernels2.cuh"
 #include "device/degk_ode_kernels3.cuh"
@@ -85,6 +86,7 @@ using namespace degk;
     {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_sde_solve<DEGK_STRICT, double, MD, ALGK>, NOV2},
 #define ERK3(NAME, MD) ODE_ERK(NAME, MD, ErkTsit5, 0) ODE_ERK(NAME, MD, ErkVern7, 1) ODE_ERK(NAME, MD, ErkVern9, 2)
 #define STIFF3(NAME, MD) ODE_ROS(NAME, MD, Rosenbrock23, 3) ODE_ROS(NAME, MD, Rodas4M, 4) ODE_ROS(NAME, MD, Rodas5PM, 5)
+#define KVAERNO2(NAME, MD) ODE_ROS(NAME, MD, Kvaerno3M, 8) ODE_ROS(NAME, MD, Kvaerno5M, 9)
 
 static const degk_aot_entry g_table[] = {
 #if DEGK_AOT_GROUP == 0
@@ -95,7 +97,7 @@ static const degk_aot_entry g_table[] = {
 #elif DEGK_AOT_GROUP == 2
     ERK3("henon_heiles", HenonHeiles)
 #elif DEGK_AOT_GROUP == 3
-    STIFF3("rober", Rober) ODE_ROS("rober", Rober, ErkTsit5, 0)
+    STIFF3("rober", Rober) ODE_ROS("rober", Rober, ErkTsit5, 0) KVAERNO2("rober", Rober)
     STIFF3("decay", Decay) ODE_ROS("decay", Decay, ErkTsit5, 0)
 #elif DEGK_AOT_GROUP == 4
     SDE("gbm", Gbm, ALG_EM, 6) SDE("gbm", Gbm, ALG_SIEA, 7)

@@ -169,7 +169,7 @@ static const degk_aot_entry* find_aot(int fp_mode, const char* model, int alg, i
 extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_program** out) {
     if (!ctx || !d || !out) return DEGK_ERR_INVALID;
     *out = nullptr;
-    if (d->alg < DEGK_ALG_TSIT5 || d->alg > DEGK_ALG_SIEA || (d->dtype != DEGK_F32 && d->dtype != DEGK_F64) ||
+    if (d->alg < DEGK_ALG_TSIT5 || d->alg > DEGK_ALG_KVAERNO5 || (d->dtype != DEGK_F32 && d->dtype != DEGK_F64) ||
         (d->fp_mode != DEGK_FP_STRICT && d->fp_mode != DEGK_FP_FAST)) {
         degk_set_error(ctx, "invalid alg/dtype/fp_mode in model description");
         return DEGK_ERR_INVALID;
@@ -355,6 +355,11 @@ static int validate(degk_program* prog, const degk_solve_args* a) {
         return DEGK_ERR_INVALID;
     }
     if (a->out_layout != DEGK_LAYOUT_REF && a->out_layout != DEGK_LAYOUT_SOA) { degk_set_error(ctx, "bad out_layout"); return DEGK_ERR_INVALID; }
+    if (a->saveat && (prog->info.alg == DEGK_ALG_KVAERNO3 || prog->info.alg == DEGK_ALG_KVAERNO5)) {
+        // the reference has no _ode_interpolant method for the Kvaerno integrators: saveat would raise there
+        degk_set_error(ctx, "GPUKvaerno3/5 have no dense output: saveat is not available (use save_everystep or endpoints)");
+        return DEGK_ERR_UNSUPPORTED;
+    }
     if (a->tstops && a->n_tstops > 0 && !prog->has_events) {
         degk_set_error(ctx, "tstops need a program built with degk_model_desc.events = 1");
         return DEGK_ERR_UNSUPPORTED;

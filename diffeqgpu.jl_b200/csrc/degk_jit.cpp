@@ -115,6 +115,7 @@ const char* method_header(int alg) {
     case DEGK_ALG_VERN7: return "gen_erk_vern7.cuh";
     case DEGK_ALG_VERN9: return "gen_erk_vern9.cuh";
     case DEGK_ALG_ROSENBROCK23: case DEGK_ALG_RODAS4: case DEGK_ALG_RODAS5P: return "degk_rosenbrock.cuh";
+    case DEGK_ALG_KVAERNO3: case DEGK_ALG_KVAERNO5: return "degk_kvaerno.cuh";
     default: return "degk_sde_kernels.cuh";
     }
 }
@@ -126,6 +127,8 @@ const char* method_type(int alg) {
     case DEGK_ALG_ROSENBROCK23: return "degk::Rosenbrock23<REAL, MODEL>";
     case DEGK_ALG_RODAS4: return "degk::Rodas<REAL, MODEL, false>";
     case DEGK_ALG_RODAS5P: return "degk::Rodas<REAL, MODEL, true>";
+    case DEGK_ALG_KVAERNO3: return "degk::Kvaerno<REAL, MODEL, false>";
+    case DEGK_ALG_KVAERNO5: return "degk::Kvaerno<REAL, MODEL, true>";
     default: return "";
     }
 }
@@ -137,6 +140,8 @@ const char* method_template(int alg) {
     case DEGK_ALG_ROSENBROCK23: return "degk::Rosenbrock23<T_, M_>";
     case DEGK_ALG_RODAS4: return "degk::Rodas<T_, M_, false>";
     case DEGK_ALG_RODAS5P: return "degk::Rodas<T_, M_, true>";
+    case DEGK_ALG_KVAERNO3: return "degk::Kvaerno<T_, M_, false>";
+    case DEGK_ALG_KVAERNO5: return "degk::Kvaerno<T_, M_, true>";
     default: return "";
     }
 }
@@ -173,13 +178,14 @@ static int save_rec_bytes(int dtype, int n_state) {
 // `slots` = trajectories per thread of the second-generation adaptive kernel (1 or 2)
 static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::string& src) {
     const bool is_sde = d->alg == DEGK_ALG_EM || d->alg == DEGK_ALG_SIEA;
-    const bool stiff = d->alg >= DEGK_ALG_ROSENBROCK23 && d->alg <= DEGK_ALG_RODAS5P;
+    const bool kvaerno = d->alg == DEGK_ALG_KVAERNO3 || d->alg == DEGK_ALG_KVAERNO5;
+    const bool stiff = (d->alg >= DEGK_ALG_ROSENBROCK23 && d->alg <= DEGK_ALG_RODAS5P) || kvaerno;
     char buf[512];
     src += "#include \"degk_common.cuh\"\n#include \"degk_pack.cuh\"\n";
     src += std::string("#include \"") + method_header(d->alg) + "\"\n";
     const bool events = d->events != 0 || d->n_callbacks > 0;
-    if (events && is_sde) {
-        degk_set_error(ctx, "tstops / callbacks are available for the ODE solvers only");
+    if (events && (is_sde || kvaerno)) {
+        degk_set_error(ctx, "tstops / callbacks are available for the explicit RK and Rosenbrock ODE solvers only");
         return DEGK_ERR_UNSUPPORTED;
     }
     if (d->n_callbacks < 0 || d->n_callbacks > 16 || (d->n_callbacks > 0 && (!d->cb_condition_src || !d->cb_affect_src))) {

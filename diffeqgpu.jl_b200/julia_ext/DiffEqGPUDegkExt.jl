@@ -46,7 +46,7 @@ end
 
 alg_id(::GPUTsit5) = 0; alg_id(::GPUVern7) = 1; alg_id(::GPUVern9) = 2
 alg_id(::GPURosenbrock23) = 3; alg_id(::GPURodas4) = 4; alg_id(::GPURodas5P) = 5
-alg_id(::GPUEM) = 6; alg_id(::GPUSIEA) = 7
+alg_id(::GPUEM) = 6; alg_id(::GPUSIEA) = 7; alg_id(::GPUKvaerno3) = 8; alg_id(::GPUKvaerno5) = 9
 dtype_id(::Type{Float32}) = 0; dtype_id(::Type{Float64}) = 1
 
 check(ctx, st) = st == 0 || error(unsafe_string(ccall((:degk_last_error, libdegk), Cstring, (Ptr{Cvoid},), ctx)))

@@ -642,7 +642,7 @@ inline void cb_affect(const SolveArgs& a, int c, T* u, T* p, T t, bool& terminat
 
 enum { RC_TERMINATED = 6 };   // ReturnCode.Terminated (terminate! in an affect, integrator_utils.jl:52-66)
 enum AlgId { A_TSIT5 = 0, A_VERN7 = 1, A_VERN9 = 2, A_ROS23 = 3, A_RODAS4 = 4, A_RODAS5P = 5,
-             A_EM = 6, A_SIEA = 7 };
+             A_EM = 6, A_SIEA = 7, A_KVAERNO3 = 8, A_KVAERNO5 = 9 };
 
 // ---- drivers: kernels.jl:1-72 (fixed) and :74-152 (adaptive) ----
 template <class T, class Integ>
@@ -718,6 +718,7 @@ void drive(Integ& I, const SolveArgs& a, int order, T t0, T tf, const T* u0, con
 }
 
 #include "oracle_stiff.inc"
+#include "oracle_kvaerno.inc"
 #include "oracle_sde.inc"
 
 template <class T>
@@ -734,6 +735,8 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
     case A_ROS23: order = 2; break;
     case A_RODAS4: order = 4; break;
     case A_RODAS5P: order = 5; break;
+    case A_KVAERNO3: order = 3; break;
+    case A_KVAERNO5: order = 5; break;
     case A_EM: case A_SIEA: break;
     default: return -2;
     }
@@ -742,7 +745,8 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
 #endif
     std::vector<T> tstops_T(a.n_tstops);
     for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
-    if ((a.n_tstops > 0 || a.n_cb > 0) && (a.alg == A_EM || a.alg == A_SIEA)) return -3;   // events: ODE steppers only
+    if ((a.n_tstops > 0 || a.n_cb > 0) && (a.alg == A_EM || a.alg == A_SIEA || a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -3;   // events: RK / Rosenbrock steppers
+    if (saveat && (a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -4;   // no dense output in the reference
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < a.n_traj; ++i) {
         const T* ui = u0 + i * a.u0_stride;
@@ -775,6 +779,17 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
             I.d = (T)1 / (two + std::sqrt(two));    // stiff/types.jl:47-48
             I.jac_mode = a.jac_mode;
             I.tstops = tstops_T.empty() ? nullptr : tstops_T.data(); I.n_tstops = (int)tstops_T.size(); I.tstops_idx = 0;
+            drive<T>(I, a, order, t0, tf, ui, out, saveat);
+            na = I.naccept; nr = I.nreject; rc = I.retcode;
+        } else if (a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5) {
+            KvInteg<T> I;
+            I.alg = a.alg; I.model = a.model; I.n = mi.n; I.pol = Policy{a.fma_stages};
+            for (int c = 0; c < mi.n; ++c) { I.u[c] = ui[c]; I.uprev[c] = ui[c]; I.k1[c] = I.k2[c] = I.k1next[c] = (T)0; }
+            for (int c = 0; c < MAXN; ++c) I.p[c] = c < mi.np ? pi[c] : (T)0;
+            I.t = t0; I.tprev = t0; I.dt = (T)a.dt; I.dtnew = (T)a.dt; I.tf = tf;
+            I.qold = (T)1.0e-4; I.abstol = (T)a.abstol; I.reltol = (T)a.reltol;
+            I.u_modified = true; I.naccept = I.nreject = I.nf = 0; I.retcode = RC_DEFAULT;
+            I.jac_mode = a.jac_mode;
             drive<T>(I, a, order, t0, tf, ui, out, saveat);
             na = I.naccept; nr = I.nreject; rc = I.retcode;
         } else {
