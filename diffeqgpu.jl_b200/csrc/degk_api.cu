@@ -188,13 +188,8 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
         const degk_aot_entry* e0 = find_aot(d->fp_mode, d->builtin, d->alg, d->dtype, 0);
         const degk_aot_entry* e1 = is_sde ? nullptr : find_aot(d->fp_mode, d->builtin, d->alg, d->dtype, 1);
         if (!e0 || (!is_sde && !e1)) {
-            use_aot = false;
-            if (!d->rhs_src) {
-                degk_set_error(ctx, "built-in model '%s' has no ahead-of-time kernel for alg %d / dtype %d "
-                                    "and no source was given for the JIT path", d->builtin, d->alg, d->dtype);
-                delete prog;
-                return DEGK_ERR_UNSUPPORTED;
-            }
+            use_aot = false;          // not every (model, solver) pair is compiled ahead of time: NVRTC builds
+                                      // the built-in's struct from the embedded degk_models.cuh instead
         } else {
             prog->fn[0] = e0->fn;
             prog->fn[1] = e1 ? e1->fn : nullptr;
@@ -480,7 +475,11 @@ static void rebuild_ts_rows(T* ts, const int32_t* nsaved, const T* saveat, const
     }
 }
 static void rebuild_ts(const degk_solve_args* a, size_t es, const int32_t* nsaved, int64_t c0, int64_t cn) {
-    const unsigned hw = std::thread::hardware_concurrency();
+    // host threads: at most 8, and the host cores are shared by the ranks of a multi-GPU job
+    // (torchrun exports LOCAL_WORLD_SIZE)
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1 && hw) hw = std::max(1u, hw / (unsigned)w); }
+    if (const char* ht = getenv("DEGK_HOST_THREADS")) { const int w = atoi(ht); if (w > 0) hw = (unsigned)w; }
     const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 4, 8), cn / 65536 + 1));
     std::vector<std::thread> th;
     for (int t = 0; t < nt; ++t) {
