@@ -75,10 +75,11 @@ using namespace degk;
     {NAME, ALG, 0, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, float, MD, METHOD>, V2(float, MD, METHOD, WF32)}, \
     {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, double, MD, METHOD>, NOV2},   \
     {NAME, ALG, 1, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, double, MD, METHOD>, V2(double, MD, METHOD, 1)},
-// Rosenbrock: scalar slots (the linear solve uses comparisons and divisions)
+// Rosenbrock: packed pairs too while the linear solve is the closed form (n <= 3: products, sums and one
+// reciprocal of the determinant); the pivoting LU of larger systems compares values and stays scalar
 #define ODE_ROS(NAME, MD, METHOD, ALG)                                                              \
     {NAME, ALG, 0, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, float, MD, METHOD>, NOV2},    \
-    {NAME, ALG, 0, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, float, MD, METHOD>, V2(float, MD, METHOD, 1)}, \
+    {NAME, ALG, 0, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, float, MD, METHOD>, V2(float, MD, METHOD, (MD::N <= 3 ? WF32 : 1))}, \
     {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, double, MD, METHOD>, NOV2},   \
     {NAME, ALG, 1, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, double, MD, METHOD>, V2(double, MD, METHOD, 1)},
 #define SDE(NAME, MD, ALGK, ALG)                                                                    \
@@ -86,7 +87,13 @@ using namespace degk;
     {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_sde_solve<DEGK_STRICT, double, MD, ALGK>, NOV2},
 #define ERK3(NAME, MD) ODE_ERK(NAME, MD, ErkTsit5, 0) ODE_ERK(NAME, MD, ErkVern7, 1) ODE_ERK(NAME, MD, ErkVern9, 2)
 #define STIFF3(NAME, MD) ODE_ROS(NAME, MD, Rosenbrock23, 3) ODE_ROS(NAME, MD, Rodas4M, 4) ODE_ROS(NAME, MD, Rodas5PM, 5)
-#define KVAERNO2(NAME, MD) ODE_ROS(NAME, MD, Kvaerno3M, 8) ODE_ROS(NAME, MD, Kvaerno5M, 9)
+#define ODE_SCALAR(NAME, MD, METHOD, ALG)                                                           \
+    {NAME, ALG, 0, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, float, MD, METHOD>, NOV2},    \
+    {NAME, ALG, 0, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, float, MD, METHOD>, V2(float, MD, METHOD, 1)}, \
+    {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, double, MD, METHOD>, NOV2},   \
+    {NAME, ALG, 1, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, double, MD, METHOD>, V2(double, MD, METHOD, 1)},
+// Kvaerno: the Newton iteration count is data dependent per trajectory -> one trajectory per thread
+#define KVAERNO2(NAME, MD) ODE_SCALAR(NAME, MD, Kvaerno3M, 8) ODE_SCALAR(NAME, MD, Kvaerno5M, 9)
 
 static const degk_aot_entry g_table[] = {
 #if DEGK_AOT_GROUP == 0

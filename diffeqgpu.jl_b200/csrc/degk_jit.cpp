@@ -154,7 +154,14 @@ int builtin_n_state(const char* name) {
 // packed pairs (2 trajectories per thread) for Float32 explicit RK in fast mode; a model whose
 // body does not compile for the packed type (e.g. it calls cos()) falls back to 1 slot
 int default_slots(const degk_model_desc* d) {
-    return (d->dtype == DEGK_F32 && d->fp_mode == DEGK_FP_FAST && d->alg <= DEGK_ALG_VERN9) ? 2 : 1;
+    if (d->dtype != DEGK_F32 || d->fp_mode != DEGK_FP_FAST) return 1;
+    if (d->alg <= DEGK_ALG_VERN9) return 2;
+    // Rosenbrock steppers: packed while the linear solve is the closed form (n <= 3) and the Jacobian is a body
+    // (the dual-number / finite-difference paths are scalar)
+    const int n = d->rhs_src ? d->n_state : builtin_n_state(d->builtin);
+    const bool has_jac = d->rhs_src ? d->jac_src != nullptr : d->jac_mode == 0;
+    if (d->alg >= DEGK_ALG_ROSENBROCK23 && d->alg <= DEGK_ALG_RODAS5P && n >= 1 && n <= 3 && has_jac) return 2;
+    return 1;
 }
 const char* builtin_struct(const char* name) {
     static const char* map[][2] = {{"lorenz", "Lorenz"}, {"henon_heiles", "HenonHeiles"}, {"rober", "Rober"},

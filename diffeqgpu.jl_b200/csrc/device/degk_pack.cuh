@@ -27,6 +27,13 @@ struct Pk2 {
     DEGK_DEV float lo() const { float a; asm("mov.b64 {%0, _}, %1;" : "=f"(a) : "l"(v)); return a; }
     DEGK_DEV float hi() const { float b; asm("mov.b64 {_, %0}, %1;" : "=f"(b) : "l"(v)); return b; }
     DEGK_DEV float get(int s) const { return s ? hi() : lo(); }
+    // math functions a model body may call, per half.  Hidden friends: found by argument-dependent
+    // lookup only, so they do not hide ::sin / ::log ... for the scalar code in this namespace
+    friend DEGK_DEV Pk2 sqrt(Pk2 a) { return Pk2(sqrtf(a.lo()), sqrtf(a.hi())); }
+    friend DEGK_DEV Pk2 sin(Pk2 a) { return Pk2(sinf(a.lo()), sinf(a.hi())); }
+    friend DEGK_DEV Pk2 cos(Pk2 a) { return Pk2(cosf(a.lo()), cosf(a.hi())); }
+    friend DEGK_DEV Pk2 exp(Pk2 a) { return Pk2(expf(a.lo()), expf(a.hi())); }
+    friend DEGK_DEV Pk2 log(Pk2 a) { return Pk2(logf(a.lo()), logf(a.hi())); }
 };
 
 DEGK_DEV Pk2 operator*(Pk2 a, Pk2 b) { Pk2 r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
@@ -36,6 +43,11 @@ DEGK_DEV Pk2 operator-(Pk2 a) { Pk2 r; r.v = a.v ^ 0x8000000080000000ull; return
 DEGK_DEV Pk2 fma_(Pk2 a, Pk2 b, Pk2 c) {
     Pk2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r;
 }
+// division / abs / sqrt per half (fast mode only: MUFU reciprocal, one packed multiply)
+DEGK_DEV Pk2 operator/(Pk2 a, Pk2 b) { return a * Pk2(rcp_(b.lo()), rcp_(b.hi())); }
+DEGK_DEV Pk2 abs_(Pk2 a) { Pk2 r; r.v = a.v & 0x7fffffff7fffffffull; return r; }
+DEGK_DEV Pk2 sqrt_(Pk2 a) { return Pk2(sqrtf(a.lo()), sqrtf(a.hi())); }
+
 // per-half select: s0 ? a.lo : b.lo , s1 ? a.hi : b.hi
 DEGK_DEV Pk2 select2(bool s0, bool s1, Pk2 a, Pk2 b) { return Pk2(s0 ? a.lo() : b.lo(), s1 ? a.hi() : b.hi()); }
 

@@ -31,10 +31,10 @@ struct LinSolve {
     int piv[N];          // n>=4: row interchanged with row k at elimination step k
 
     DEGK_DEV bool factor(const T (&A)[N][N]) {
-        if (N == 1) {
+        if constexpr (N == 1) {
             dinv[0] = (T)1 / A[0][0];
             return true;
-        } else if (N == 2) {
+        } else if constexpr (N == 2) {
             const T d = A[0][0] * A[1][1] - A[0][1] * A[1][0];
 #if DEGK_STRICT
             dinv[0] = d;
@@ -43,7 +43,7 @@ struct LinSolve {
 #endif
             lu[0][0] = A[1][1]; lu[0][1] = A[0][1]; lu[1][0] = A[1][0]; lu[1][1] = A[0][0];
             return true;
-        } else if (N == 3) {
+        } else if constexpr (N == 3) {
             const T a11 = A[0][0], a12 = A[0][1], a13 = A[0][2];
             const T a21 = A[1][0], a22 = A[1][1], a23 = A[1][2];
             const T a31 = A[2][0], a32 = A[2][1], a33 = A[2][2];
@@ -93,9 +93,9 @@ struct LinSolve {
     }
 
     DEGK_DEV void solve(const T (&b)[N], T (&x)[N]) const {
-        if (N == 1) {
+        if constexpr (N == 1) {
             x[0] = dinv[0] * b[0];
-        } else if (N == 2) {
+        } else if constexpr (N == 2) {
 #if DEGK_STRICT
             x[0] = (lu[0][0] * b[0] - lu[0][1] * b[1]) / dinv[0];
             x[1] = (lu[1][1] * b[1] - lu[1][0] * b[0]) / dinv[0];
@@ -103,7 +103,7 @@ struct LinSolve {
             x[0] = (lu[0][0] * b[0] - lu[0][1] * b[1]) * dinv[0];
             x[1] = (lu[1][1] * b[1] - lu[1][0] * b[0]) * dinv[0];
 #endif
-        } else if (N == 3) {
+        } else if constexpr (N == 3) {
             DEGK_UNROLL for (int i = 0; i < 3; ++i) {
                 const T s = (lu[i][0] * b[0] + lu[i][1] * b[1]) + lu[i][2] * b[2];
 #if DEGK_STRICT
