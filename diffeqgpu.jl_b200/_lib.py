@@ -37,7 +37,7 @@ class ModelDesc(C.Structure):
                 ("fp_mode", C.c_int32), ("force_jit", C.c_int32),
                 ("events", C.c_int32), ("n_callbacks", C.c_int32),
                 ("cb_condition_src", C.POINTER(C.c_char_p)), ("cb_affect_src", C.POINTER(C.c_char_p)),
-                ("jac_mode", C.c_int32), ("reserved", C.c_int32)]
+                ("jac_mode", C.c_int32), ("reserved", C.c_int32), ("mass_src", C.c_char_p)]
 
 
 class ProgramInfo(C.Structure):
@@ -128,13 +128,14 @@ def _b(s):
 
 def make_desc(*, builtin=None, rhs_src=None, jac_src=None, tgrad_src=None, noise_src=None,
               n_state=0, n_param=0, n_noise=0, noise_kind=NOISE_NONE, dtype=F32, alg=0,
-              fp_mode=FP_STRICT, force_jit=False, events=False, callbacks=(), jac_mode=0):
+              fp_mode=FP_STRICT, force_jit=False, events=False, callbacks=(), jac_mode=0, mass_src=None):
     """callbacks: sequence of (condition_src, affect_src) CUDA-C bodies (degk.h, degk_model_desc)."""
     d = ModelDesc(_b(builtin), _b(rhs_src), _b(jac_src), _b(tgrad_src), _b(noise_src),
                   n_state, n_param, n_noise, noise_kind, dtype, alg, fp_mode, int(force_jit))
     d.events = int(bool(events) or len(callbacks) > 0)
     d.n_callbacks = len(callbacks)
     d.jac_mode = int(jac_mode)
+    d.mass_src = _b(mass_src)
     if callbacks:
         conds = (C.c_char_p * len(callbacks))(*[_b(c[0]) for c in callbacks])
         affs = (C.c_char_p * len(callbacks))(*[_b(c[1]) for c in callbacks])

@@ -146,7 +146,7 @@ const char* method_template(int alg) {
     }
 }
 int builtin_n_state(const char* name) {
-    static const struct { const char* n; int N; } dims[] = {{"lorenz", 3}, {"henon_heiles", 4}, {"rober", 3}, {"decay", 1},
+    static const struct { const char* n; int N; } dims[] = {{"lorenz", 3}, {"henon_heiles", 4}, {"rober", 3}, {"rober_dae", 3}, {"decay", 1},
         {"linear15", 15}, {"gbm", 3}, {"scalar_sde", 1}, {"osc_t", 2}, {"gbm_nd", 2}};
     for (auto& m : dims) if (name && strcmp(m.n, name) == 0) return m.N;
     return 0;
@@ -164,7 +164,7 @@ int default_slots(const degk_model_desc* d) {
     return 1;
 }
 const char* builtin_struct(const char* name) {
-    static const char* map[][2] = {{"lorenz", "Lorenz"}, {"henon_heiles", "HenonHeiles"}, {"rober", "Rober"},
+    static const char* map[][2] = {{"lorenz", "Lorenz"}, {"henon_heiles", "HenonHeiles"}, {"rober", "Rober"}, {"rober_dae", "RoberDae"},
                                    {"decay", "Decay"}, {"linear15", "Linear15"}, {"gbm", "Gbm"},
                                    {"scalar_sde", "ScalarSde"}, {"osc_t", "OscT"}, {"gbm_nd", "GbmNd"}};
     for (auto& m : map) if (strcmp(m[0], name) == 0) return m[1];
@@ -237,6 +237,17 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
             src += "    template <class T> static DEGK_DEV void tgrad(T (&dT)[N], const T (&u)[N], const T* p, T t) {\n"
                    "        DEGK_UNROLL for (int i_ = 0; i_ < N; ++i_) dT[i_] = (T)0;\n";
             if (d->tgrad_src) src += d->tgrad_src;
+            src += "\n    }\n";
+        }
+        if (d->mass_src) {
+            if (d->alg != DEGK_ALG_ROSENBROCK23) {
+                degk_set_error(ctx, "mass matrices are lowered for GPURosenbrock23 only (the solver the reference tests them with)");
+                return DEGK_ERR_UNSUPPORTED;
+            }
+            src += "    static constexpr bool HAS_MASS = true;\n"
+                   "    template <class T> static DEGK_DEV void mass(T (&Mm)[N][N]) {\n"
+                   "        DEGK_UNROLL for (int i_ = 0; i_ < N; ++i_) DEGK_UNROLL for (int j_ = 0; j_ < N; ++j_) Mm[i_][j_] = (T)0;\n";
+            src += d->mass_src;
             src += "\n    }\n";
         }
         if (noise == DEGK_NOISE_DIAGONAL) {
@@ -414,7 +425,7 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     } else {
         // dims of a JIT-compiled built-in: mirror of degk_models.cuh
         static const struct { const char* n; int N, NP, M, K; } dims[] = {
-            {"lorenz", 3, 3, 3, 1}, {"henon_heiles", 4, 0, 0, 0}, {"rober", 3, 3, 0, 0}, {"decay", 1, 1, 0, 0},
+            {"lorenz", 3, 3, 3, 1}, {"henon_heiles", 4, 0, 0, 0}, {"rober", 3, 3, 0, 0}, {"rober_dae", 3, 3, 0, 0}, {"decay", 1, 1, 0, 0},
             {"linear15", 15, 0, 0, 0}, {"gbm", 3, 2, 3, 1}, {"scalar_sde", 1, 2, 1, 1}, {"osc_t", 2, 1, 0, 0},
             {"gbm_nd", 2, 2, 4, 2}};
         for (auto& m : dims)

@@ -74,6 +74,20 @@ template <class...> struct void_t_ { typedef void type; };
 template <class M, class = void> struct jac_mode_of { static constexpr int value = JAC_FORWARD_AD; };
 template <class M> struct jac_mode_of<M, typename void_t_<decltype(M::JAC_MODE)>::type> { static constexpr int value = M::JAC_MODE; };
 
+// constant mass matrix (reference: ODEFunction(f; mass_matrix = M), src/utils.jl:42-57): models that
+// have one define HAS_MASS = true and mass(Mm); everything else is the identity (UniformScaling)
+template <class M, class = void> struct has_mass_of { static constexpr bool value = false; };
+template <class M> struct has_mass_of<M, typename void_t_<decltype(M::HAS_MASS)>::type> { static constexpr bool value = M::HAS_MASS; };
+// StaticArrays SMatrix * SVector: row sums as a left fold of the products
+template <class T, int N>
+DEGK_DEV void mass_mul(const T (&Mm)[N][N], const T (&v)[N], T (&out)[N]) {
+    DEGK_UNROLL for (int i = 0; i < N; ++i) {
+        T s = Mm[i][0] * v[0];
+        DEGK_UNROLL for (int j = 1; j < N; ++j) s = s + Mm[i][j] * v[j];
+        out[i] = s;
+    }
+}
+
 template <class T> DEGK_DEV T sqrt_eps_();
 template <> DEGK_DEV float sqrt_eps_<float>() { return 3.4526698300124393e-4f; }      // sqrt(eps(Float32))
 template <> DEGK_DEV double sqrt_eps_<double>() { return 1.4901161193847656e-8; }     // sqrt(eps(Float64))

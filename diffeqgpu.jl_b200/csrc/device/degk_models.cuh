@@ -64,6 +64,27 @@ struct Rober {
     }
 };
 
+// Robertson in DAE form with mass matrix diag(1, 1, 0): test/gpu_kernel_de/stiff_ode/gpu_ode_mass_matrix.jl:5-31
+struct RoberDae {
+    static constexpr int N = 3, NP = 3, M = 0, NOISE = 0;
+    static constexpr bool HAS_JAC = true, HAS_TGRAD = true, HAS_MASS = true;
+    template <class T> static DEGK_DEV void f(T (&du)[N], const T (&u)[N], const T* p, T t) {
+        du[0] = -p[0] * u[0] + p[2] * u[1] * u[2];
+        du[1] = p[0] * u[0] - p[1] * (u[1] * u[1]) - p[2] * u[1] * u[2];
+        du[2] = u[0] + u[1] + u[2] - (T)1;
+    }
+    template <class T> static DEGK_DEV void jac(T (&J)[N][N], const T (&u)[N], const T* p, T t) {
+        J[0][0] = p[0] * (T)-1;  J[0][1] = u[2] * p[2];                                    J[0][2] = p[2] * u[1];
+        J[1][0] = p[0];          J[1][1] = u[1] * p[1] * (T)-2 + u[2] * p[2] * (T)-1;      J[1][2] = p[2] * u[1] * (T)-1;
+        J[2][0] = (T)1;          J[2][1] = (T)1;                                           J[2][2] = (T)1;
+    }
+    template <class T> static DEGK_DEV void tgrad(T (&dT)[N], const T (&u)[N], const T* p, T t) { dT[0] = dT[1] = dT[2] = (T)0; }
+    template <class T> static DEGK_DEV void mass(T (&Mm)[N][N]) {
+        DEGK_UNROLL for (int i = 0; i < N; ++i) DEGK_UNROLL for (int j = 0; j < N; ++j) Mm[i][j] = (T)0;
+        Mm[0][0] = (T)1; Mm[1][1] = (T)1;
+    }
+};
+
 struct Decay {
     static constexpr int N = 1, NP = 1, M = 0, NOISE = 0;
     static constexpr bool HAS_JAC = true, HAS_TGRAD = true;

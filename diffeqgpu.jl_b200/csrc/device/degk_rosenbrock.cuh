@@ -158,11 +158,19 @@ struct Rosenbrock23 {
         T J[N][N], W[N][N], dT[N];
         eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
         eval_tgrad<T, Model>(dT, uprev, p, t);
-        DEGK_UNROLL for (int i = 0; i < N; ++i)
-            DEGK_UNROLL for (int j = 0; j < N; ++j) {
-                const T v = -(gam * J[i][j]);
-                W[i][j] = (i == j) ? v + (T)1 : v;
-            }
+        constexpr bool MASS = has_mass_of<Model>::value;     // W = mass_matrix - gamma*J (:45, :120)
+        T Mm[MASS ? N : 1][MASS ? N : 1];
+        if constexpr (MASS) {
+            Model::template mass<T>(Mm);
+            DEGK_UNROLL for (int i = 0; i < N; ++i)
+                DEGK_UNROLL for (int j = 0; j < N; ++j) W[i][j] = Mm[i][j] - gam * J[i][j];
+        } else {
+            DEGK_UNROLL for (int i = 0; i < N; ++i)
+                DEGK_UNROLL for (int j = 0; j < N; ++j) {
+                    const T v = -(gam * J[i][j]);
+                    W[i][j] = (i == j) ? v + (T)1 : v;
+                }
+        }
         LinSolve<T, N> F;
         if (!F.factor(W)) return false;
         T F0[N], F1[N], rhs[N], tmp[N];
@@ -171,7 +179,13 @@ struct Rosenbrock23 {
         F.solve(rhs, K.k1);
         DEGK_UNROLL for (int c = 0; c < N; ++c) tmp[c] = uprev[c] + dto2 * K.k1[c];
         Model::template f<T>(F1, tmp, p, t + dto2);
-        DEGK_UNROLL for (int c = 0; c < N; ++c) rhs[c] = F1[c] - K.k1[c];
+        if constexpr (MASS) {                                // F1 - mass_matrix * k1 (:57, :132)
+            T mk[N];
+            mass_mul<T, N>(Mm, K.k1, mk);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) rhs[c] = F1[c] - mk[c];
+        } else {
+            DEGK_UNROLL for (int c = 0; c < N; ++c) rhs[c] = F1[c] - K.k1[c];
+        }
         F.solve(rhs, K.k2);
         DEGK_UNROLL for (int c = 0; c < N; ++c) K.k2[c] = K.k2[c] + K.k1[c];
         DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uprev[c] + h * K.k2[c];
@@ -179,8 +193,17 @@ struct Rosenbrock23 {
             const T e32 = (T)6 + sqrt_((T)2);
             T F2[N], k3[N];
             Model::template f<T>(F2, unew, p, t + h);
-            DEGK_UNROLL for (int c = 0; c < N; ++c)
-                rhs[c] = ((F2[c] - e32 * (K.k2[c] - F1[c])) - two * (K.k1[c] - F0[c])) + h * dT[c];
+            if constexpr (MASS) {
+                // F2 - mass_matrix * (e32*k2 + 2*k1) + e32*F1 + 2*F0 + dt*dT  (:144-148)
+                T v[N], mv[N];
+                DEGK_UNROLL for (int c = 0; c < N; ++c) v[c] = e32 * K.k2[c] + two * K.k1[c];
+                mass_mul<T, N>(Mm, v, mv);
+                DEGK_UNROLL for (int c = 0; c < N; ++c)
+                    rhs[c] = (((F2[c] - mv[c]) + e32 * F1[c]) + two * F0[c]) + h * dT[c];
+            } else {
+                DEGK_UNROLL for (int c = 0; c < N; ++c)
+                    rhs[c] = ((F2[c] - e32 * (K.k2[c] - F1[c])) - two * (K.k1[c] - F0[c])) + h * dT[c];
+            }
             F.solve(rhs, k3);
             DEGK_UNROLL for (int c = 0; c < N; ++c) err[c] = dto6 * ((K.k1[c] - two * K.k2[c]) + k3[c]);
         }
@@ -225,6 +248,7 @@ struct Rodas {
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
                                  T (&unew)[N], T (&err)[N]) {
+        static_assert(!has_mass_of<Model>::value, "mass matrices are lowered for GPURosenbrock23 only");
         T J[N][N], dT[N];
         eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
         eval_tgrad<T, Model>(dT, uprev, p, t);

@@ -25,6 +25,7 @@ struct ModelDesc
     events::Int32; n_callbacks::Int32                 # tstops / GPUDiscreteCallback lowering (degk.h)
     cb_condition_src::Ptr{Cstring}; cb_affect_src::Ptr{Cstring}
     jac_mode::Int32; reserved::Int32                  # 0 analytic/default, 1 finite differences, 2 ForwardDiff-style duals
+    mass_src::Cstring                                 # constant mass matrix body (GPURosenbrock23), C_NULL = identity
 end
 
 struct SolveArgs

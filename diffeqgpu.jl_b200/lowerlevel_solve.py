@@ -78,7 +78,7 @@ def _convert_saveat_adaptive(saveat, prob):
 
 
 def _model_key(f):
-    return (f.builtin, f.rhs, f.jac, f.tgrad, f.n_state, f.n_param, f.force_jit, f.use_jac)
+    return (f.builtin, f.rhs, f.jac, f.tgrad, f.n_state, f.n_param, f.force_jit, f.use_jac, f.mass_matrix)
 
 
 def _jac_mode(f, alg):
@@ -115,7 +115,7 @@ def get_program(prob, alg, fp_mode="strict", device=None, callback=None, events=
         desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, jac_src=jac_src, tgrad_src=f.tgrad if jac_mode == 0 else None,
                               n_state=f.n_state, n_param=f.n_param, dtype=dtype, alg=alg.alg_id,
                               fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit, events=events,
-                              callbacks=cbs.key(), jac_mode=jac_mode)
+                              callbacks=cbs.key(), jac_mode=jac_mode, mass_src=f.mass_matrix)
     return ctx.program(desc, key)
 
 

@@ -57,6 +57,21 @@ linear15 = ODEFunction(builtin="linear15", force_jit=True, python=lambda u, p, t
 linear15_src = ODEFunction(rhs=LINEAR15_RHS, jac=LINEAR15_JAC, n_state=15, n_param=0,
                            python=lambda u, p, t: 1.01 * np.asarray(u))
 
+# Robertson as a DAE with mass matrix diag(1, 1, 0): test/gpu_kernel_de/stiff_ode/gpu_ode_mass_matrix.jl:5-31
+ROBER_DAE_RHS = """
+    du[0] = -p[0] * u[0] + p[2] * u[1] * u[2];
+    du[1] = p[0] * u[0] - p[1] * (u[1] * u[1]) - p[2] * u[1] * u[2];
+    du[2] = u[0] + u[1] + u[2] - (T)1;
+"""
+ROBER_DAE_JAC = """
+    J[0][0] = p[0] * (T)-1;  J[0][1] = u[2] * p[2];                                J[0][2] = p[2] * u[1];
+    J[1][0] = p[0];          J[1][1] = u[1] * p[1] * (T)-2 + u[2] * p[2] * (T)-1;  J[1][2] = p[2] * u[1] * (T)-1;
+    J[2][0] = (T)1;          J[2][1] = (T)1;                                       J[2][2] = (T)1;
+"""
+rober_dae = ODEFunction(builtin="rober_dae", force_jit=True)
+rober_dae_src = ODEFunction(rhs=ROBER_DAE_RHS, jac=ROBER_DAE_JAC, mass_matrix="    Mm[0][0] = (T)1; Mm[1][1] = (T)1;\n",
+                            n_state=3, n_param=3)
+
 # test/gpu_kernel_de/finite_diff.jl:6-9 / forward_diff.jl: du = -p u^2, NO analytic Jacobian: the stiff
 # solvers differentiate it (forward-mode duals, or finite differences with autodiff = False)
 QUAD_DECAY_RHS = "    du[0] = -p[0] * u[0] * u[0];\n"

@@ -36,6 +36,7 @@ class ODEFunction:
     n_param: int = 0
     python: Optional[Callable] = field(default=None, compare=False)
     force_jit: bool = False
+    mass_matrix: Optional[str] = None   # body assigning Mm[i][j] of a constant mass matrix (GPURosenbrock23), None = identity
     use_jac: bool = True      # False: ignore the analytic Jacobian (the function "has no jac"), for the AD / FD paths
 
     def __post_init__(self):
@@ -55,7 +56,7 @@ class SDEFunction:
 
 
 BUILTIN_DIMS = {  # name -> (n_state, n_param, n_noise, noise_kind); mirror of degk_models.cuh
-    "lorenz": (3, 3, 3, 1), "henon_heiles": (4, 0, 0, 0), "rober": (3, 3, 0, 0),
+    "lorenz": (3, 3, 3, 1), "henon_heiles": (4, 0, 0, 0), "rober": (3, 3, 0, 0), "rober_dae": (3, 3, 0, 0),
     "decay": (1, 1, 0, 0), "linear15": (15, 0, 0, 0), "gbm": (3, 2, 3, 1),
     "scalar_sde": (1, 2, 1, 1), "osc_t": (2, 1, 0, 0), "gbm_nd": (2, 2, 4, 2),
 }

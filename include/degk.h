@@ -134,6 +134,10 @@ typedef struct {
      * 2 = forward-mode duals.  On a built-in model 1 and 2 ignore its analytic Jacobian. */
     int32_t jac_mode;
     int32_t reserved;
+    /* constant mass matrix M of  M u' = f(u, p, t)  (ODEFunction(f; mass_matrix = M), src/utils.jl:42-57):
+     * body assigning Mm[i][j] (zero-initialised), NULL = identity.  GPURosenbrock23 only (the solver the
+     * reference's mass-matrix test uses); u0 must be consistent (no DAE initialisation). */
+    const char* mass_src;
 } degk_model_desc;
 
 typedef struct {
