@@ -231,26 +231,41 @@ def main():
     if not args.no_e2e:
         cap = int(100e9 / world / (BYTES_OUT + BYTES_IN))
         Ne = min(N, cap)
-        p_host = torch.empty((Ne, 3), dtype=torch.float32, pin_memory=True)
-        p_host.copy_(p[:Ne])
-        us_h = torch.empty((Ne, 11, 3), dtype=torch.float32, pin_memory=True)
-        ts_h = torch.empty((Ne, 11), dtype=torch.float32, pin_memory=True)
-        hk = dict(p=p_host, dt=f32(0.1), adaptive=True, abstol=1e-6, reltol=1e-6, saveat=SAVEAT, fp_mode=args.fp,
-                  schedule=args.schedule, out={"us": us_h, "ts": ts_h}, stats="totals", device=dev, chunk_traj=1 << 21)
-        _, _, hst = dg.solve_host(prob, alg, **hk)        # warm-up (allocates workspaces)
-        att_e = int(hst["totals"][0] + hst["totals"][1])
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            dg.solve_host(prob, alg, **hk)
-        torch.cuda.synchronize(dev)
-        t_e = max_over_ranks(time.perf_counter() - t0, dev)
-        tot_e = sum_over_ranks(att_e, dev) * args.e2e_steps
-        e2e = {"value": tot_e / t_e, "unit": "trajectory-steps/s", "h2d_bytes_per_step": int(Ne * BYTES_IN + 44 + 20),
-               "d2h_bytes_per_step": int(Ne * (132 + 4)), "traj_per_gpu": Ne, "ms_per_step": 1e3 * t_e / args.e2e_steps,
-               "note": "degk_solve_host: pinned host buffers, 2M-trajectory chunks over 3 streams; us (132 B/trajectory) "
-                       "and one row count (4 B) come back over PCIe, the (len x N) ts array is rebuilt in host memory "
-                       "from the row counts inside the timed region; host clock around the blocking call, max over ranks"}
+        # pinned host buffers: 188 B per trajectory and rank.  If the box cannot pin that much (many ranks
+        # share one host), halve the end-to-end batch instead of losing the whole bench line; every rank
+        # takes the smallest size any rank managed.
+        p_host = us_h = ts_h = None
+        while Ne >= 1_000_000:
+            try:
+                p_host = torch.empty((Ne, 3), dtype=torch.float32, pin_memory=True)
+                us_h = torch.empty((Ne, 11, 3), dtype=torch.float32, pin_memory=True)
+                ts_h = torch.empty((Ne, 11), dtype=torch.float32, pin_memory=True)
+                break
+            except RuntimeError:
+                p_host = us_h = ts_h = None
+                Ne //= 2
+        Ne_all = int(-max_over_ranks(-float(Ne if p_host is not None else 0), dev))     # min over ranks
+        if Ne_all >= 1_000_000:
+            if Ne_all != Ne:
+                Ne = Ne_all
+                p_host, us_h, ts_h = p_host[:Ne], us_h[:Ne], ts_h[:Ne]
+            p_host.copy_(p[:Ne])
+            hk = dict(p=p_host, dt=f32(0.1), adaptive=True, abstol=1e-6, reltol=1e-6, saveat=SAVEAT, fp_mode=args.fp,
+                      schedule=args.schedule, out={"us": us_h, "ts": ts_h}, stats="totals", device=dev, chunk_traj=1 << 21)
+            _, _, hst = dg.solve_host(prob, alg, **hk)        # warm-up (allocates workspaces)
+            att_e = int(hst["totals"][0] + hst["totals"][1])
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                dg.solve_host(prob, alg, **hk)
+            torch.cuda.synchronize(dev)
+            t_e = max_over_ranks(time.perf_counter() - t0, dev)
+            tot_e = sum_over_ranks(att_e, dev) * args.e2e_steps
+            e2e = {"value": tot_e / t_e, "unit": "trajectory-steps/s", "h2d_bytes_per_step": int(Ne * BYTES_IN + 44 + 20),
+                   "d2h_bytes_per_step": int(Ne * (132 + 4)), "traj_per_gpu": Ne, "ms_per_step": 1e3 * t_e / args.e2e_steps,
+                   "note": "degk_solve_host: pinned host buffers, 2M-trajectory chunks over 3 streams; us (132 B/trajectory) "
+                           "and one row count (4 B) come back over PCIe, the (len x N) ts array is rebuilt in host memory "
+                           "from the row counts inside the timed region; host clock around the blocking call, max over ranks"}
         del p_host, us_h, ts_h
 
     if world > 1:
