@@ -18,7 +18,8 @@ from ._lib import DegkError
 from .algorithms import (EnsembleGPUKernel, GPUEM, GPUKvaerno3, GPUKvaerno5, GPUODEAlgorithm, GPUODEImplicitAlgorithm,
                          GPURodas4, GPURodas5P, GPURosenbrock23, GPUSDEAlgorithm, GPUSIEA,
                          GPUTsit5, GPUVern7, GPUVern9, alg_order)
-from .callbacks import CallbackSet, ContinuousCallback, DiscreteCallback, GPUDiscreteCallback
+from .callbacks import (CallbackSet, ContinuousCallback, DiscreteCallback, GPUContinuousCallback,
+                        GPUDiscreteCallback)
 from .lowerlevel_solve import Range, get_program, vectorized_asolve, vectorized_solve
 from .problems import (EnsembleContext, EnsembleProblem, ODEFunction, ODEProblem, ProblemBatch,
                        SDEFunction, SDEProblem, adapt, make_prob_compatible, remake)
@@ -31,5 +32,5 @@ __all__ = [
     "vectorized_solve", "EnsembleContext", "EnsembleProblem", "ODEFunction", "ODEProblem",
     "ProblemBatch", "SDEFunction", "SDEProblem", "adapt", "make_prob_compatible", "remake",
     "EnsembleSolution", "ODESolution", "solve", "solve_host", "models",
-    "GPUKvaerno3", "GPUKvaerno5", "CallbackSet", "ContinuousCallback", "DiscreteCallback", "GPUDiscreteCallback",
+    "GPUKvaerno3", "GPUKvaerno5", "CallbackSet", "ContinuousCallback", "GPUContinuousCallback", "DiscreteCallback", "GPUDiscreteCallback",
 ]

@@ -37,7 +37,12 @@ class ModelDesc(C.Structure):
                 ("fp_mode", C.c_int32), ("force_jit", C.c_int32),
                 ("events", C.c_int32), ("n_callbacks", C.c_int32),
                 ("cb_condition_src", C.POINTER(C.c_char_p)), ("cb_affect_src", C.POINTER(C.c_char_p)),
-                ("jac_mode", C.c_int32), ("reserved", C.c_int32), ("mass_src", C.c_char_p)]
+                ("jac_mode", C.c_int32), ("reserved", C.c_int32), ("mass_src", C.c_char_p),
+                ("n_ccallbacks", C.c_int32), ("reserved3", C.c_int32),
+                ("cc_condition_src", C.POINTER(C.c_char_p)), ("cc_affect_src", C.POINTER(C.c_char_p)),
+                ("cc_affect_neg_src", C.POINTER(C.c_char_p)), ("cc_rootfind", C.POINTER(C.c_int32)),
+                ("cc_abstol", C.POINTER(C.c_double)), ("cc_repeat_nudge", C.POINTER(C.c_double)),
+                ("cc_dtrelax", C.POINTER(C.c_double))]
 
 
 class ProgramInfo(C.Structure):
@@ -128,7 +133,7 @@ def _b(s):
 
 def make_desc(*, builtin=None, rhs_src=None, jac_src=None, tgrad_src=None, noise_src=None,
               n_state=0, n_param=0, n_noise=0, noise_kind=NOISE_NONE, dtype=F32, alg=0,
-              fp_mode=FP_STRICT, force_jit=False, events=False, callbacks=(), jac_mode=0, mass_src=None):
+              fp_mode=FP_STRICT, force_jit=False, events=False, callbacks=(), jac_mode=0, mass_src=None, ccallbacks=()):
     """callbacks: sequence of (condition_src, affect_src) CUDA-C bodies (degk.h, degk_model_desc)."""
     d = ModelDesc(_b(builtin), _b(rhs_src), _b(jac_src), _b(tgrad_src), _b(noise_src),
                   n_state, n_param, n_noise, noise_kind, dtype, alg, fp_mode, int(force_jit))
@@ -136,6 +141,18 @@ def make_desc(*, builtin=None, rhs_src=None, jac_src=None, tgrad_src=None, noise
     d.n_callbacks = len(callbacks)
     d.jac_mode = int(jac_mode)
     d.mass_src = _b(mass_src)
+    # ccallbacks: sequence of (condition_src, affect_src | None, affect_neg_src | None, rootfind, abstol, repeat_nudge, dtrelax)
+    d.n_ccallbacks = len(ccallbacks)
+    if ccallbacks:
+        n = len(ccallbacks)
+        arrs = ((C.c_char_p * n)(*[_b(c[0]) for c in ccallbacks]), (C.c_char_p * n)(*[_b(c[1]) for c in ccallbacks]),
+                (C.c_char_p * n)(*[_b(c[2]) for c in ccallbacks]), (C.c_int32 * n)(*[int(c[3]) for c in ccallbacks]),
+                (C.c_double * n)(*[float(c[4]) for c in ccallbacks]), (C.c_double * n)(*[float(c[5]) for c in ccallbacks]),
+                (C.c_double * n)(*[float(c[6]) for c in ccallbacks]))
+        (d.cc_condition_src, d.cc_affect_src, d.cc_affect_neg_src, d.cc_rootfind, d.cc_abstol, d.cc_repeat_nudge,
+         d.cc_dtrelax) = arrs
+        d.events = 1
+        d._keepalive_cc = arrs
     if callbacks:
         conds = (C.c_char_p * len(callbacks))(*[_b(c[0]) for c in callbacks])
         affs = (C.c_char_p * len(callbacks))(*[_b(c[1]) for c in callbacks])

@@ -182,7 +182,7 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
     memset(&prog->info, 0, sizeof prog->info);
     prog->info.dtype = d->dtype; prog->info.alg = d->alg; prog->info.fp_mode = d->fp_mode;
 
-    bool use_aot = d->builtin && !d->force_jit && !d->events && d->n_callbacks == 0 &&   // event kernels are JIT-built
+    bool use_aot = d->builtin && !d->force_jit && !d->events && d->n_callbacks == 0 && d->n_ccallbacks == 0 &&   // event kernels are JIT-built
                    d->jac_mode == 0;
     if (use_aot) {
         const degk_aot_entry* e0 = find_aot(d->fp_mode, d->builtin, d->alg, d->dtype, 0);

@@ -190,7 +190,7 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
     char buf[512];
     src += "#include \"degk_common.cuh\"\n#include \"degk_pack.cuh\"\n";
     src += std::string("#include \"") + method_header(d->alg) + "\"\n";
-    const bool events = d->events != 0 || d->n_callbacks > 0;
+    const bool events = d->events != 0 || d->n_callbacks > 0 || d->n_ccallbacks > 0;
     if (events && (is_sde || kvaerno)) {
         degk_set_error(ctx, "tstops / callbacks are available for the explicit RK and Rosenbrock ODE solvers only");
         return DEGK_ERR_UNSUPPORTED;
@@ -304,7 +304,54 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
         src += "        default: return false;\n        }\n    }\n";
         src += "    template <class T> static DEGK_DEV void affect(int c, T (&u)[N], T* p, T t, bool& terminate_) {\n        switch (c) {\n";
         for (int c = 0; c < d->n_callbacks; ++c) { snprintf(buf, sizeof buf, "        case %d: affect%d<T>(u, p, t, terminate_); break;\n", c, c); src += buf; }
-        src += "        default: break;\n        }\n    }\n};\n}\n";
+        src += "        default: break;\n        }\n    }\n";
+        // continuous callbacks
+        if (d->n_ccallbacks < 0 || d->n_ccallbacks > 8 || (d->n_ccallbacks > 0 && !d->cc_condition_src)) {
+            degk_set_error(ctx, "n_ccallbacks must be in 0..8 with condition sources");
+            return DEGK_ERR_INVALID;
+        }
+        if (d->n_ccallbacks > 0 && stiff) {
+            degk_set_error(ctx, "continuous callbacks are lowered for the explicit RK solvers");
+            return DEGK_ERR_UNSUPPORTED;
+        }
+        snprintf(buf, sizeof buf, "    static constexpr int NCC = %d;\n", d->n_ccallbacks);
+        src += buf;
+        for (int c = 0; c < d->n_ccallbacks; ++c) {
+            if (!d->cc_condition_src[c]) { degk_set_error(ctx, "continuous callback %d: NULL condition", c); return DEGK_ERR_INVALID; }
+            snprintf(buf, sizeof buf, "    template <class T> static DEGK_DEV T ccondition%d(const T (&u)[N], const T* p, T t) {\n", c);
+            src += buf; src += d->cc_condition_src[c]; src += "\n    }\n";
+            for (int neg = 0; neg < 2; ++neg) {
+                const char* body = neg ? (d->cc_affect_neg_src ? d->cc_affect_neg_src[c] : nullptr) : (d->cc_affect_src ? d->cc_affect_src[c] : nullptr);
+                snprintf(buf, sizeof buf, "    template <class T> static DEGK_DEV void caffect%d_%d(T (&u)[N], T* p, T t, bool& terminate_) {\n"
+                                          "#define terminate() (terminate_ = true)\n", c, neg);
+                src += buf; if (body) src += body; src += "\n#undef terminate\n    }\n";
+            }
+        }
+        src += "    template <class T> static DEGK_DEV T ccondition(int c, const T (&u)[N], const T* p, T t) {\n        switch (c) {\n";
+        for (int c = 0; c < d->n_ccallbacks; ++c) { snprintf(buf, sizeof buf, "        case %d: return ccondition%d<T>(u, p, t);\n", c, c); src += buf; }
+        src += "        default: return (T)1;\n        }\n    }\n";
+        src += "    template <class T> static DEGK_DEV void caffect(int c, bool neg, T (&u)[N], T* p, T t, bool& terminate_) {\n        switch (2 * c + (neg ? 1 : 0)) {\n";
+        for (int c = 0; c < d->n_ccallbacks; ++c)
+            for (int neg = 0; neg < 2; ++neg) { snprintf(buf, sizeof buf, "        case %d: caffect%d_%d<T>(u, p, t, terminate_); break;\n", 2 * c + neg, c, neg); src += buf; }
+        src += "        default: break;\n        }\n    }\n";
+        auto table = [&](const char* sig, const char* deflt, auto value) {
+            src += std::string("    static DEGK_DEV ") + sig + " {\n        switch (c) {\n";
+            for (int c = 0; c < d->n_ccallbacks; ++c) { char b2[160]; snprintf(b2, sizeof b2, "        case %d: return %s;\n", c, value(c).c_str()); src += b2; }
+            src += std::string("        default: return ") + deflt + ";\n        }\n    }\n";
+        };
+        auto dbl = [](double v) { char b2[64]; snprintf(b2, sizeof b2, "%.17g", v); return std::string(b2); };
+        src += "    static DEGK_DEV bool has_caffect(int c, bool neg) {\n        switch (2 * c + (neg ? 1 : 0)) {\n";
+        for (int c = 0; c < d->n_ccallbacks; ++c)
+            for (int neg = 0; neg < 2; ++neg) {
+                const bool has = neg ? (d->cc_affect_neg_src && d->cc_affect_neg_src[c]) : (d->cc_affect_src && d->cc_affect_src[c]);
+                snprintf(buf, sizeof buf, "        case %d: return %s;\n", 2 * c + neg, has ? "true" : "false"); src += buf;
+            }
+        src += "        default: return false;\n        }\n    }\n";
+        table("int rootfind(int c)", "0", [&](int c) { return std::to_string(d->cc_rootfind ? d->cc_rootfind[c] : 0); });
+        table("double cc_abstol(int c)", "0.0", [&](int c) { return dbl(d->cc_abstol ? d->cc_abstol[c] : 10 * 1.1920928955078125e-7); });
+        table("double cc_repeat_nudge(int c)", "0.0", [&](int c) { return dbl(d->cc_repeat_nudge ? d->cc_repeat_nudge[c] : 0.01); });
+        table("double cc_dtrelax(int c)", "1.0", [&](int c) { return dbl(d->cc_dtrelax ? d->cc_dtrelax[c] : 1.0); });
+        src += "};\n}\n";
         src += "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
                "    degk::ode_solve_events_body<REAL, MODEL, METHOD, degk::UserCallbacks>(a);\n}\n"
                "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_adaptive(const degk::KArgs a) {\n"
@@ -406,7 +453,7 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     // f1 (first-generation adaptive kernel) is not part of JIT builds
     prog->jit_fn[0] = f0;
     prog->jit_fn[1] = f1;
-    const bool events = d->events != 0 || d->n_callbacks > 0;
+    const bool events = d->events != 0 || d->n_callbacks > 0 || d->n_ccallbacks > 0;
     prog->has_events = events;
     CUfunction f2 = nullptr;
     if (events) {

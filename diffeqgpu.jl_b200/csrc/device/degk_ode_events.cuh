@@ -14,10 +14,24 @@
 // spliced in by NVRTC (degk_jit.cpp), so the programs that use them are JIT-built and carry this
 // pair of kernels in place of the generation-2/3 adaptive kernel.
 //
+// Continuous callbacks (GPUContinuousCallback, callbacks.jl:38-124) run first, as in handle_callbacks!:
+// find_callback_time (integrator_utils.jl:383-442: sign change of the condition between tprev --
+// nudged by repeat_nudge*dt off a root found in the previous step -- and t, dense output in between),
+// the hand-written ITP root finder gpu_find_root (:326-381), the earliest event over the set
+// (DiffEqBase.find_first_continuous_callback -- not vendored; restated from the published package),
+// then apply_callback! (:232-269): move (t, u) back to the event by interpolation, save, mark
+// u_modified and run affect! / affect_neg! by the sign before the event.  Two in-tree quirks are
+// kept: the affects of continuous_callbacks[1] run whichever callback fired (:296-301), and
+// last_event_error is never updated (stays 0).
+//
 // CB is a struct with
-//   static constexpr int NCB;
+//   static constexpr int NCB, NCC;
 //   template <class T> static bool condition(int c, const T (&u)[N], const T* p, T t);
 //   template <class T> static void affect(int c, T (&u)[N], T* p, T t, bool& terminate_);
+//   template <class T> static T    ccondition(int c, const T (&u)[N], const T* p, T t);
+//   template <class T> static void caffect(int c, bool neg, T (&u)[N], T* p, T t, bool& terminate_);
+//   static bool has_caffect(int c, bool neg);  static int rootfind(int c);     // 0 Left, 1 Right, 2 None
+//   static double cc_abstol(int c), cc_repeat_nudge(int c), cc_dtrelax(int c);
 #pragma once
 #include "degk_common.cuh"
 
@@ -26,10 +40,118 @@ namespace degk {
 enum { RC_TERMINATED = 6 };
 
 struct NoCallbacks {
-    static constexpr int NCB = 0;
+    static constexpr int NCB = 0, NCC = 0;
     template <class T, int N> static DEGK_DEV bool condition(int, const T (&)[N], const T*, T) { return false; }
     template <class T, int N> static DEGK_DEV void affect(int, T (&)[N], T*, T, bool&) {}
+    template <class T, int N> static DEGK_DEV T ccondition(int, const T (&)[N], const T*, T) { return (T)1; }
+    template <class T, int N> static DEGK_DEV void caffect(int, bool, T (&)[N], T*, T, bool&) {}
+    static DEGK_DEV bool has_caffect(int, bool) { return false; }
+    static DEGK_DEV int rootfind(int) { return 0; }
+    static DEGK_DEV double cc_abstol(int) { return 0.0; }
+    static DEGK_DEV double cc_repeat_nudge(int) { return 0.0; }
+    static DEGK_DEV double cc_dtrelax(int) { return 1.0; }
 };
+
+// Base.sign, Base.eps(x), nextfloat for the ITP root finder
+template <class T> DEGK_DEV T sign_(T x) { return x > (T)0 ? (T)1 : (x < (T)0 ? (T)-1 : x); }
+DEGK_DEV float eps_of(float x) {
+    if (!finite_(x)) return x - x;
+    const float ax = fabsf(x);
+    return ax >= 1.17549435e-38f ? ldexpf(1.1920928955078125e-7f, ilogbf(ax)) : 1.401298464e-45f;
+}
+DEGK_DEV double eps_of(double x) {
+    if (!finite_(x)) return x - x;
+    const double ax = fabs(x);
+    return ax >= 2.2250738585072014e-308 ? ldexp(2.220446049250313e-16, ilogb(ax)) : 4.9406564584124654e-324;
+}
+DEGK_DEV float next_up(float x) { return nextafterf(x, __int_as_float(0x7f800000)); }
+DEGK_DEV double next_up(double x) { return nextafter(x, __longlong_as_double(0x7ff0000000000000LL)); }
+DEGK_DEV float copysign_(float a, float b) { return copysignf(a, b); }
+DEGK_DEV double copysign_(double a, double b) { return copysign(a, b); }
+
+// gpu_find_root (integrator_utils.jl:326-381): ITP with scaled_k1 = 0.2, k2 = 2, n0 = 10
+template <class T, class F>
+DEGK_DEV T itp_root(F&& fz, T left, T right, int rootfind) {
+    T fl = fz(left), fr = fz(right);
+    const T span0 = right - left;
+    const T k1 = (T)0.2 / span0;
+    T eps_s = span0 * (T)512;
+    for (int it = 0; it < 100; ++it) {
+        const T span = right - left;
+        const T mid = (left + right) / (T)2;
+        const T r = eps_s - span / (T)2;
+        const T x_f = left + span * fl / (fl - fr);
+        const T delta = jl_max(k1 * span * span, eps_of(x_f));
+        const T diff = mid - x_f;
+        const T xt = (delta <= abs_(diff)) ? x_f + copysign_(delta, diff) : mid;
+        const T xp = (abs_(xt - mid) <= r) ? xt : mid - copysign_(r, diff);
+        const T yp = fz(xp);
+        const T yps = yp * sign_(fr);
+        if (yps > (T)0) { right = xp; fr = yp; }
+        else if (yps < (T)0) { left = xp; fl = yp; }
+        else { left = xp; right = xp; break; }
+        eps_s = eps_s / (T)2;
+        if (next_up(left) >= right) break;
+    }
+    return rootfind == 0 ? left : right;
+}
+
+// handle_callbacks!, continuous part.  hdt = integ.dt (the step the dense output belongs to); dtnew is
+// the adaptive integrator's next step (nullptr for fixed dt).  Returns saved_in_cb.
+template <class T, class Model, class Method, class CB, class SaveF>
+DEGK_DEV bool handle_continuous(const typename Method::Keep& K, T (&u)[Model::N], const T (&uprev)[Model::N], T* p,
+                                T& t, T tprev, T hdt, T tf, T* dtnew, i64& step_idx, int& event_last_time,
+                                bool& u_modified, bool& terminated, SaveF&& savevalues) {
+    constexpr int N = Model::N;
+    const T last_event_error = (T)0;
+    auto get_condition = [&](int c, T abst) -> T {       // :460-479
+        if (abst == t) return CB::ccondition(c, u, p, abst);
+        if (abst == tprev) return CB::ccondition(c, uprev, p, abst);
+        T v[N];
+        Method::interp(K, (abst - tprev) / hdt, hdt, uprev, u, p, tprev, v);
+        return CB::ccondition(c, v, p, abst);
+    };
+    bool occurred = false;
+    T tmin = t, up = (T)0;
+    int idx = 0;
+    DEGK_UNROLL for (int c = 0; c < CB::NCC; ++c) {
+        T bottom_t = tprev;
+        T bottom_condition = CB::ccondition(c, uprev, p, tprev);
+        if (event_last_time == c + 1 && abs_(bottom_condition - last_event_error) <= (T)CB::cc_abstol(c)) {
+            bottom_t = tprev + hdt * (T)CB::cc_repeat_nudge(c);
+            bottom_condition = get_condition(c, bottom_t);
+        }
+        const T bottom_sign = sign_(bottom_condition);
+        const T top_t = t;
+        const T top_sign = sign_(get_condition(c, top_t));
+        const bool ev = ((bottom_sign < (T)0 && CB::has_caffect(c, false)) || (bottom_sign > (T)0 && CB::has_caffect(c, true))) &&
+                        bottom_sign * top_sign <= (T)0;
+        if (ev) {
+            T cbt;
+            if (CB::rootfind(c) == 2 || top_sign == (T)0) cbt = top_t;
+            else cbt = itp_root<T>([&](T x) { return get_condition(c, x); }, bottom_t, top_t, CB::rootfind(c));
+            if (cbt < tmin || !occurred) { tmin = cbt; up = bottom_sign; occurred = true; idx = c + 1; }
+        }
+    }
+    if (!occurred) { event_last_time = 0; return false; }
+    event_last_time = idx;
+    if (tmin != t) {                                     // change_t_via_interpolation!, :186-206
+        T v[N];
+        Method::interp(K, (tmin - tprev) / hdt, hdt, uprev, u, p, tprev, v);
+        step_idx -= (i64)rint((double)((t - tmin) / hdt));
+        DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = v[c];
+        t = tmin;
+    }
+    if (dtnew != nullptr && *dtnew < (T)1.0e-12) {        // :240-249
+        const T remaining = abs_(tf - t);
+        *dtnew = jl_min((T)CB::cc_dtrelax(0) * hdt, remaining);
+    }
+    savevalues();
+    u_modified = true;
+    if (up < (T)0) { if (!CB::has_caffect(0, false)) u_modified = false; else CB::caffect(0, false, u, p, t, terminated); }
+    else if (up > (T)0) { if (!CB::has_caffect(0, true)) u_modified = false; else CB::caffect(0, true, u, p, t, terminated); }
+    return true;
+}
 
 // eps(T) of `T(100) * eps(T)` in the tstops test
 template <class T> DEGK_DEV T eps_();
@@ -77,6 +199,7 @@ DEGK_DEV void ode_solve_events_body(const KArgs& a) {
         int rc = RC_SUCCESS;
         int tstops_idx = 0;
         bool first = true, u_modified = false, terminated = false;
+        int event_last_time = 0;
         i64 iters = 0;
         // savevalues! (integrator_utils.jl:13-50)
         auto savevalues = [&]() {
@@ -122,6 +245,10 @@ DEGK_DEV void ode_solve_events_body(const KArgs& a) {
             DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = unew[c];
             ++nsteps;
             bool saved_in_cb = false;
+            if (CB::NCC > 0)
+                saved_in_cb = handle_continuous<T, Model, Method, CB>(K, u, uprev, p, t, tprev, dt, tf, (T*)nullptr, step_idx,
+                                                                      event_last_time, u_modified, terminated, savevalues);
+            if (CB::NCB > 0) saved_in_cb = false;    // handle_callbacks! returns the discrete pass's flag (:318-326)
             DEGK_UNROLL for (int c = 0; c < CB::NCB; ++c) {
                 if (CB::condition(c, u, p, t)) {
                     savevalues();
@@ -197,6 +324,8 @@ DEGK_DEV void ode_asolve_events_body(const KArgs& a) {
         int rc = RC_DEFAULT;
         int tstops_idx = 0;
         bool first = true, u_modified = false, terminated = false;
+        int event_last_time = 0;
+        i64 dummy_step_idx = 1;      // adaptive integrators do not save every step (Q3)
         i64 iters = 0;
         auto savevalues = [&]() {    // adaptive integrators are built with save_everystep = false (Q3)
             if (has_saveat) {
@@ -262,7 +391,7 @@ DEGK_DEV void ode_asolve_events_body(const KArgs& a) {
                     ++tstops_idx;
                 } else {
                     t = tcur + h;
-                    if (t == tcur) t = tf;                   // see DESIGN.md, deviations (sub-ulp remaining span)
+                    if (t == tcur && (tf - tcur - h) <= h) t = tf;   // see DESIGN.md, deviations (sub-ulp remaining span)
                 }
                 h = dtnew;
                 ++nacc;
@@ -270,6 +399,10 @@ DEGK_DEV void ode_asolve_events_body(const KArgs& a) {
             }
             if (rc != RC_DEFAULT) break;
             bool saved_in_cb = false;
+            if (CB::NCC > 0)
+                saved_in_cb = handle_continuous<T, Model, Method, CB>(K, u, uprev, p, t, tprev, step_dt, tf, &h, dummy_step_idx,
+                                                                      event_last_time, u_modified, terminated, savevalues);
+            if (CB::NCB > 0) saved_in_cb = false;
             DEGK_UNROLL for (int c = 0; c < CB::NCB; ++c) {
                 if (CB::condition(c, u, p, t)) {
                     savevalues();

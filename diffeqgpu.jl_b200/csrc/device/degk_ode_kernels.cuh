@@ -291,7 +291,7 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                     // a step that cannot advance t (remaining span below ulp(t)) lands on tf: the
                     // reference would loop forever here (deviations)
                     T tnew = ((tf - t - h) < Method::land()) ? tf : t + h;
-                    if (tnew == t) tnew = tf;
+                    if (tnew == t && (tf - t - h) <= h) tnew = tf;
                     ++nacc;
                     Method::on_accept(K);
                     if (has_saveat) {                        // integrator_utils.jl:34-47

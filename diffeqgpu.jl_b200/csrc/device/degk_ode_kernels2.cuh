@@ -343,7 +343,7 @@ DEGK_DEV void ode_asolve2_body(const KArgs& a, unsigned char* smem_raw) {
             // a step that cannot advance t (remaining span below ulp(t)) lands on tf: the reference
             // would loop forever here (deviations)
             const T tsum = t[s] + h[s];
-            const T tn = ((rem < MethodS::land()) | (tsum == t[s])) ? tf[s] : tsum;
+            const T tn = ((rem < MethodS::land()) | ((tsum == t[s]) & (rem <= h[s]))) ? tf[s] : tsum;
             T h_next, lq_next;
             bool reject;
 #if DEGK_STRICT

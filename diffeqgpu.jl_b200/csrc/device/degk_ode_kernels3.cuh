@@ -375,7 +375,7 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
             const T rem_s = PO::get(rem, s), tsum_s = PO::get(tsum, s), hf_s = PO::get(hf, s);
             // land on tf (gpu_tsit5_perform_step.jl:155-156); a step that cannot advance t
             // (remaining span below ulp(t)) lands too -- the reference would loop forever
-            const bool land = (rem_s < MethodS::land()) | (tsum_s == t[s]);
+            const bool land = (rem_s < MethodS::land()) | ((tsum_s == t[s]) & (rem_s <= h[s]));
             const T tn = land ? tf[s] : tsum_s;
             hnext_[s] = rej[s] ? hf_s : fmin_(abs_(hf_s), abs_(rem_s));
             const bool live = h[s] >= dtmin;                     // dead slots carry h < dtmin

@@ -111,11 +111,11 @@ def get_program(prob, alg, fp_mode="strict", device=None, callback=None, events=
     else:
         f = prob.f
         jac_mode, jac_src = _jac_mode(f, alg)
-        key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode, events, cbs.key(), jac_mode)
+        key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode, events, cbs.key(), cbs.ckey(), jac_mode)
         desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, jac_src=jac_src, tgrad_src=f.tgrad if jac_mode == 0 else None,
                               n_state=f.n_state, n_param=f.n_param, dtype=dtype, alg=alg.alg_id,
                               fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit, events=events,
-                              callbacks=cbs.key(), jac_mode=jac_mode, mass_src=f.mass_matrix)
+                              callbacks=cbs.key(), jac_mode=jac_mode, mass_src=f.mass_matrix, ccallbacks=cbs.ckey())
     return ctx.program(desc, key)
 
 

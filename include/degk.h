@@ -138,6 +138,20 @@ typedef struct {
      * body assigning Mm[i][j] (zero-initialised), NULL = identity.  GPURosenbrock23 only (the solver the
      * reference's mass-matrix test uses); u0 must be consistent (no DAE initialisation). */
     const char* mass_src;
+    /* Continuous callbacks (GPUContinuousCallback, callbacks.jl:38-124; same kernels as `events`).
+     * cc_condition_src[c]: body RETURNING the value of condition(u, t, integrator) (a root function);
+     * cc_affect_src[c] / cc_affect_neg_src[c]: bodies of affect! (sign - -> +) and affect_neg! (+ -> -),
+     * a NULL entry = `nothing`; cc_rootfind[c]: 0 LeftRootFind, 1 RightRootFind, 2 NoRootFind;
+     * cc_abstol / cc_repeat_nudge / cc_dtrelax: the callback's fields (defaults 10eps(Float32), 1//100, 1). */
+    int32_t n_ccallbacks;
+    int32_t reserved3;
+    const char* const* cc_condition_src;
+    const char* const* cc_affect_src;
+    const char* const* cc_affect_neg_src;
+    const int32_t* cc_rootfind;
+    const double* cc_abstol;
+    const double* cc_repeat_nudge;
+    const double* cc_dtrelax;
 } degk_model_desc;
 
 typedef struct {

@@ -86,7 +86,8 @@ template <class T> inline T thresh(double lit, int via_f32) {
 enum ModelId { M_LORENZ = 0, M_HENON_HEILES = 1, M_ROBER = 2, M_DECAY = 3, M_LINEAR15 = 4,
                M_GBM = 5, M_LORENZ_ADDITIVE = 6, M_SCALAR_SDE = 7, M_OSC_T = 8, M_GBM_ND = 9,
                M_QUAD_DECAY = 10,
-               M_ROBER_DAE = 11 };    // Robertson DAE + mass matrix diag(1,1,0): stiff_ode/gpu_ode_mass_matrix.jl:5-31   // du = -p u^2: test/gpu_kernel_de/finite_diff.jl:6-9, forward_diff.jl
+               M_ROBER_DAE = 11,
+               M_BALL = 12 };         // bouncing ball x'' = -g: test/gpu_kernel_de/gpu_ode_continuous_callbacks.jl:6-10    // Robertson DAE + mass matrix diag(1,1,0): stiff_ode/gpu_ode_mass_matrix.jl:5-31   // du = -p u^2: test/gpu_kernel_de/finite_diff.jl:6-9, forward_diff.jl
 
 struct ModelInfo { int n, np, m; bool has_jac; bool diag_noise; };
 
@@ -104,6 +105,7 @@ inline ModelInfo model_info(int id) {
     case M_GBM_ND:          return {2, 2, 4, false, false};  // 2x4 non-diagonal noise
     case M_QUAD_DECAY:      return {1, 1, 0, true, true};
     case M_ROBER_DAE:       return {3, 3, 0, true, true};
+    case M_BALL:            return {2, 1, 0, true, true};
     }
     return {0, 0, 0, false, true};
 }
@@ -189,6 +191,10 @@ inline void model_f(int id, T* du, const T* u, const T* p, T t) {
         du[1] = p[0] * u[0] - p[1] * (u[1] * u[1]) - p[2] * u[1] * u[2];
         du[2] = u[0] + u[1] + u[2] - (T)1;
         break;
+    case M_BALL:
+        du[0] = u[1];
+        du[1] = -p[0];
+        break;
     }
 }
 
@@ -228,6 +234,9 @@ inline void model_jac(int id, T (*J)[MAXN], const T* u, const T* p, T t) {
         break;
     case M_QUAD_DECAY:
         J[0][0] = (T)-2 * p[0] * u[0];
+        break;
+    case M_BALL:
+        J[0][1] = (T)1;
         break;
     case M_ROBER_DAE:      // the test passes no jac (ForwardDiff); rows 1-2 as rober_jac (:14-22), row 3 of the constraint
         J[0][0] = p[0] * (T)-1;  J[0][1] = u[2] * p[2];                                J[0][2] = p[2] * u[1];
@@ -599,7 +608,7 @@ struct ErkInteg {
                 interpolant((t - tprev) / dt, dt, v);
                 for (int c = 0; c < n; ++c) u[c] = v[c];
                 ++tstops_idx;
-            } else { t = tcur + h; if (t == tcur) t = tf; }
+            } else { t = tcur + h; if (t == tcur && (tf - tcur - h) <= h) t = tf; }
             ++naccept;
             return true;
         }
@@ -631,7 +640,67 @@ struct SolveArgs {
     int n_tstops = 0; const double* tstops = nullptr;
     int n_cb = 0; const int32_t* cb_i = nullptr; const double* cb_v = nullptr;
     int jac_mode = 0;   // stiff steppers: 0 analytic jac/tgrad, 1 finite differences, 2 forward-mode duals
+    // continuous callbacks (GPUContinuousCallback, callbacks.jl:38-124):
+    // cc_i[8*c + ..] = condition kind, condition index, affect kind (-1 = nothing), affect index,
+    //                  affect_neg kind (-1 = nothing), affect_neg index, rootfind (0 Left, 1 Right, 2 None), 0
+    // cc_v[6*c + ..] = condition value, affect value, affect_neg value, abstol, repeat_nudge, dtrelax
+    int n_cc = 0; const int32_t* cc_i = nullptr; const double* cc_v = nullptr;
 };
+
+// continuous condition kinds: 0 u[i] - v | 1 t - v
+template <class T>
+inline T cc_condition(const SolveArgs& a, int c, const T* u, T t) {
+    const int kind = a.cc_i[8 * c], idx = a.cc_i[8 * c + 1];
+    const T v = (T)a.cc_v[6 * c];
+    return kind == 0 ? u[idx] - v : t - v;
+}
+template <class T>
+inline void cc_affect(const SolveArgs& a, int c, bool neg, T* u, T* p, bool& terminated) {
+    const int kind = a.cc_i[8 * c + (neg ? 4 : 2)], idx = a.cc_i[8 * c + (neg ? 5 : 3)];
+    const T v = (T)a.cc_v[6 * c + (neg ? 2 : 1)];
+    switch (kind) {
+    case 0: u[idx] = u[idx] + v; break;
+    case 1: u[idx] = v; break;
+    case 2: u[idx] = u[idx] * v; break;
+    case 3: terminated = true; break;
+    default: p[idx] = v; break;
+    }
+}
+template <class T> inline T sign_(T x) { return x > (T)0 ? (T)1 : (x < (T)0 ? (T)-1 : x); }   // Base.sign
+template <class T> inline T eps_of(T x) {      // Base.eps(x::AbstractFloat)
+    if (!std::isfinite((double)x)) return std::numeric_limits<T>::quiet_NaN();
+    const T ax = std::fabs(x);
+    if (ax >= std::numeric_limits<T>::min()) return std::ldexp(std::numeric_limits<T>::epsilon(), std::ilogb(ax));
+    return std::numeric_limits<T>::denorm_min();
+}
+
+// gpu_find_root: hand-written ITP, integrator_utils.jl:326-381 (scaled_k1 = 0.2, k2 = 2, n0 = 10)
+template <class T, class F>
+inline T itp_root(F&& fz, T left, T right, int rootfind) {
+    T fl = fz(left), fr = fz(right);
+    const T span0 = right - left;
+    const T k1 = (T)0.2 / span0;
+    T eps_s = span0 * (T)512;
+    for (int it = 0; it < 100; ++it) {
+        const T span = right - left;
+        const T mid = (left + right) / (T)2;
+        const T r = eps_s - span / (T)2;
+        const T x_f = left + span * fl / (fl - fr);
+        const T delta = jl_max(k1 * span * span, eps_of<T>(x_f));
+        const T diff = mid - x_f;
+        const T xt = (delta <= std::fabs(diff)) ? x_f + std::copysign(delta, diff) : mid;
+        const T xp = (std::fabs(xt - mid) <= r) ? xt : mid - std::copysign(r, diff);
+        const T yp = fz(xp);
+        const T yps = yp * sign_(fr);
+        if (yps > (T)0) { right = xp; fr = yp; }
+        else if (yps < (T)0) { left = xp; fl = yp; }
+        else { left = xp; right = xp; break; }
+        eps_s = eps_s / (T)2;
+        if (std::nextafter(left, std::numeric_limits<T>::infinity()) >= right) break;
+    }
+    return rootfind == 0 ? left : right;
+}
+
 
 // condition kinds: 0 t == v | 1 u[i] < v | 2 u[i] > v | 3 t >= v
 // affect kinds:    0 u[i] += v | 1 u[i] = v | 2 u[i] *= v | 3 terminate!(integrator) | 4 p[i] = v
@@ -694,8 +763,64 @@ void drive(Integ& I, const SolveArgs& a, int order, T t0, T tf, const T* u0, con
     };
     // handle_callbacks! -> apply_discrete_callback! (integrator_utils.jl:69-96, 271-330): each
     // callback whose condition holds saves first, then sets u_modified and runs its affect
+    // continuous callbacks: find_callback_time (integrator_utils.jl:383-442), the earliest event over the
+    // set (DiffEqBase.find_first_continuous_callback), apply_callback! (:232-269) -- which always runs
+    // continuous_callbacks[1]'s affects (in-tree quirk, :296-301)
+    int event_last_time = 0;
+    const T last_event_error = (T)0;             // never updated by the in-tree handle_callbacks!
+    auto get_condition = [&](int c, T abst) -> T {        // :460-479
+        if (abst == I.t) return cc_condition<T>(a, c, I.u, abst);
+        if (abst == I.tprev) return cc_condition<T>(a, c, I.uprev, abst);
+        T v[MAXN];
+        I.interpolant((abst - I.tprev) / I.dt, I.dt, v);
+        return cc_condition<T>(a, c, v, abst);
+    };
+    auto continuous = [&]() -> bool {
+        bool occurred = false;
+        T tmin = I.t, up = (T)0;
+        int idx = 0;
+        for (int c = 0; c < a.n_cc; ++c) {
+            const T cc_abstol = (T)a.cc_v[6 * c + 3], nudge = (T)a.cc_v[6 * c + 4];
+            const int rootfind = a.cc_i[8 * c + 6];
+            T bottom_t = I.tprev;
+            T bottom_condition = cc_condition<T>(a, c, I.uprev, I.tprev);
+            if (event_last_time == c + 1 && std::fabs(bottom_condition - last_event_error) <= cc_abstol) {
+                bottom_t = I.tprev + I.dt * nudge;        // nudge off the previous root
+                bottom_condition = get_condition(c, bottom_t);
+            }
+            const T bottom_sign = sign_(bottom_condition);
+            const T top_t = I.t;
+            const T top_sign = sign_(get_condition(c, top_t));
+            const bool ev = ((bottom_sign < (T)0 && a.cc_i[8 * c + 2] >= 0) || (bottom_sign > (T)0 && a.cc_i[8 * c + 4] >= 0)) &&
+                            bottom_sign * top_sign <= (T)0;
+            if (!ev) continue;
+            T cbt;
+            if (rootfind == 2 || top_sign == (T)0) cbt = top_t;
+            else cbt = itp_root<T>([&](T x) { return get_condition(c, x); }, bottom_t, top_t, rootfind);
+            if (cbt < tmin || !occurred) { tmin = cbt; up = bottom_sign; occurred = true; idx = c + 1; }
+        }
+        if (!occurred) { event_last_time = 0; return false; }
+        event_last_time = idx;
+        if (tmin != I.t) {                                // change_t_via_interpolation!, :186-206
+            T v[MAXN];
+            I.interpolant((tmin - I.tprev) / I.dt, I.dt, v);
+            for (int c = 0; c < I.n; ++c) I.u[c] = v[c];
+            step_idx -= (int64_t)std::nearbyint((double)((I.t - tmin) / I.dt));
+            I.t = tmin;
+        }
+        if (a.adaptive && I.dtnew < (T)1.0e-12) {          // :240-249
+            const T remaining = std::fabs(I.tf - I.t);
+            I.dtnew = jl_min((T)a.cc_v[5] * I.dt, remaining);
+        }
+        savevalues();
+        I.u_modified = true;
+        if (up < (T)0) { if (a.cc_i[2] < 0) I.u_modified = false; else cc_affect<T>(a, 0, false, I.u, I.p, terminated); }
+        else if (up > (T)0) { if (a.cc_i[4] < 0) I.u_modified = false; else cc_affect<T>(a, 0, true, I.u, I.p, terminated); }
+        return true;
+    };
     auto callbacks = [&]() -> bool {
-        bool saved_in_cb = false;
+        bool saved_in_cb = a.n_cc > 0 ? continuous() : false;
+        if (a.n_cb > 0) saved_in_cb = false;          // handle_callbacks! takes saved_in_cb of the discrete pass (:318-326)
         for (int c = 0; c < a.n_cb; ++c) {
             if (cb_condition<T>(a, c, I.u, I.p, I.t)) {
                 savevalues();
@@ -766,7 +891,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
 #endif
     std::vector<T> tstops_T(a.n_tstops);
     for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
-    if ((a.n_tstops > 0 || a.n_cb > 0) && (a.alg == A_EM || a.alg == A_SIEA || a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -3;   // events: RK / Rosenbrock steppers
+    if ((a.n_tstops > 0 || a.n_cb > 0 || a.n_cc > 0) && (a.alg == A_EM || a.alg == A_SIEA || a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -3;   // events: RK / Rosenbrock steppers
     if (saveat && (a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -4;   // no dense output in the reference
     if (a.model == M_ROBER_DAE && a.alg != A_ROS23) return -5;              // mass matrices: Rosenbrock23 only
 #pragma omp parallel for schedule(dynamic, 64)
@@ -865,7 +990,7 @@ int degk_oracle_solve_events(int dtype, int model, int alg, int adaptive, int64_
                              int32_t* naccept, int32_t* nreject, int32_t* retcode,
                              int fma_stages, int nthreads,
                              const double* tstops, int n_tstops, const int32_t* cb_i, const double* cb_v, int n_cb,
-                             int jac_mode) {
+                             int jac_mode, const int32_t* cc_i, const double* cc_v, int n_cc) {
     SolveArgs a;
     a.model = model; a.alg = alg; a.adaptive = adaptive; a.save_everystep = save_everystep;
     a.nsave = nsave; a.fma_stages = fma_stages; a.n_traj = n_traj; a.len = len;
@@ -874,6 +999,7 @@ int degk_oracle_solve_events(int dtype, int model, int alg, int adaptive, int64_
     a.max_iters = 10000000;
     a.tstops = tstops; a.n_tstops = n_tstops; a.cb_i = cb_i; a.cb_v = cb_v; a.n_cb = n_cb;
     a.jac_mode = jac_mode;
+    a.cc_i = cc_i; a.cc_v = cc_v; a.n_cc = n_cc;
     if (dtype == 0)
         return solve_T<float>(a, (const float*)u0, (const float*)p, (const float*)tspan,
                               (const float*)saveat, (float*)us, (float*)ts, naccept, nreject,

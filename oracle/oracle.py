@@ -14,7 +14,7 @@ _LIB_PATH = _HERE / "_build" / "libdegk_oracle.so"
 _SRCS = ("degk_oracle.cpp", "oracle_stiff.inc", "oracle_kvaerno.inc", "oracle_sde.inc", "oracle_tables.inc")
 
 MODELS = {"lorenz": 0, "henon_heiles": 1, "rober": 2, "decay": 3, "linear15": 4, "gbm": 5,
-          "lorenz_additive": 6, "scalar_sde": 7, "osc_t": 8, "gbm_nd": 9, "quad_decay": 10, "rober_dae": 11}
+          "lorenz_additive": 6, "scalar_sde": 7, "osc_t": 8, "gbm_nd": 9, "quad_decay": 10, "rober_dae": 11, "ball": 12}
 ALGS = {"tsit5": 0, "vern7": 1, "vern9": 2, "rosenbrock23": 3, "rodas4": 4, "rodas5p": 5,
         "em": 6, "siea": 7, "kvaerno3": 8, "kvaerno5": 9}
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
@@ -22,6 +22,7 @@ RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "M
 # discrete-callback specs shared with tests/cases.py (which lowers them to CUDA-C for the device)
 COND_KINDS = {"t_eq": 0, "u_lt": 1, "u_gt": 2, "t_ge": 3}
 AFFECT_KINDS = {"u_add": 0, "u_set": 1, "u_scale": 2, "terminate": 3, "p_set": 4}
+CC_COND_KINDS = {"u_minus": 0, "t_minus": 1}      # continuous conditions: u[i] - v, t - v
 
 _lib = None
 
@@ -52,7 +53,8 @@ def lib():
             ctypes.c_int, ctypes.c_int]
         _lib.degk_oracle_solve_events.restype = ctypes.c_int
         _lib.degk_oracle_solve_events.argtypes = _lib.degk_oracle_solve.argtypes + [
-            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _lib.degk_oracle_num_threads.restype = ctypes.c_int
     return _lib
 
@@ -70,7 +72,7 @@ def _ptr(a):
 
 def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3,
           saveat=None, save_everystep=True, length=None, seed=0, dtype=np.float32,
-          fma_stages=False, nthreads=0, tstops=None, callbacks=(), jac_mode=0):
+          fma_stages=False, nthreads=0, tstops=None, callbacks=(), jac_mode=0, continuous_callbacks=()):
     """Solve a batch; returns dict(ts=(N,len), us=(N,len,n), naccept, nreject, retcode).
 
     u0: (N,n) or (n,) broadcast; p: (N,np) or (np,) broadcast; tspan: (2,) or (N,2).
@@ -111,7 +113,7 @@ def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1
             float(dtype.type(dt)), float(dtype.type(abstol)), float(dtype.type(reltol)),
             _ptr(saveat), 0 if saveat is None else len(saveat), int(save_everystep), int(seed),
             _ptr(us), _ptr(ts), length, _ptr(na), _ptr(nr), _ptr(rc), int(fma_stages), int(nthreads)]
-    if tstops is not None or len(callbacks) or jac_mode:
+    if tstops is not None or len(callbacks) or jac_mode or len(continuous_callbacks):
         # tstops reach the integrator already converted to the time type (adapt(backend, tstops))
         tst = np.ascontiguousarray([] if tstops is None else np.asarray(tstops, dtype=dtype), dtype=np.float64)
         cb_i = np.zeros((max(len(callbacks), 1), 4), np.int32)
@@ -119,7 +121,24 @@ def solve(model, alg, u0, p, tspan, *, dt, adaptive=False, abstol=1e-6, reltol=1
         for c, ((ck, ci, cv), (ak, ai, av)) in enumerate(callbacks):
             cb_i[c] = (COND_KINDS[ck], ci, AFFECT_KINDS[ak], ai)
             cb_v[c] = (float(dtype.type(cv)), float(dtype.type(av)))
-        r = lib().degk_oracle_solve_events(*args, _ptr(tst), len(tst), _ptr(cb_i), _ptr(cb_v), len(callbacks), int(jac_mode))
+        # continuous callbacks: dict(condition=(kind, idx, val), affect=(kind, idx, val) | None,
+        #   affect_neg=(kind, idx, val) | None | "same", rootfind="left"|"right"|"none", abstol, repeat_nudge, dtrelax)
+        cc_i = np.zeros((max(len(continuous_callbacks), 1), 8), np.int32)
+        cc_v = np.zeros((max(len(continuous_callbacks), 1), 6), np.float64)
+        for c, cc in enumerate(continuous_callbacks):
+            ck, ci, cv = cc["condition"]
+            aff = cc.get("affect")
+            neg = cc.get("affect_neg", "same")
+            neg = aff if neg == "same" else neg
+            cc_i[c] = (CC_COND_KINDS[ck], ci, -1 if aff is None else AFFECT_KINDS[aff[0]], 0 if aff is None else aff[1],
+                       -1 if neg is None else AFFECT_KINDS[neg[0]], 0 if neg is None else neg[1],
+                       {"left": 0, "right": 1, "none": 2}[cc.get("rootfind", "left")], 0)
+            cc_v[c] = (float(dtype.type(cv)), 0.0 if aff is None else float(dtype.type(aff[2])),
+                       0.0 if neg is None else float(dtype.type(neg[2])),
+                       float(dtype.type(cc.get("abstol", 10 * np.finfo(np.float32).eps))),
+                       float(dtype.type(cc.get("repeat_nudge", 0.01))), float(dtype.type(cc.get("dtrelax", 1))))
+        r = lib().degk_oracle_solve_events(*args, _ptr(tst), len(tst), _ptr(cb_i), _ptr(cb_v), len(callbacks), int(jac_mode),
+                                           _ptr(cc_i), _ptr(cc_v), len(continuous_callbacks))
     else:
         r = lib().degk_oracle_solve(*args)
     if r != 0:

@@ -65,3 +65,22 @@ def callback_sources(spec, dtype=np.float32):
            "u_scale": f"u[{ai}] = u[{ai}] * {_lit(av, dtype)};", "terminate": "terminate();",
            "p_set": f"p[{ai}] = {_lit(av, dtype)};"}[ak]
     return cond, aff
+
+
+def continuous_callback_sources(cc, dtype=np.float32):
+    """cc: oracle-style dict(condition=(kind, idx, val), affect=..., affect_neg=..., rootfind, ...) ->
+    kwargs of dg.ContinuousCallback (condition / affect bodies in CUDA-C)"""
+    ck, ci, cv = cc["condition"]
+    cond = {"u_minus": f"return u[{ci}] - {_lit(cv, dtype)};", "t_minus": f"return t - {_lit(cv, dtype)};"}[ck]
+
+    def aff(a):
+        if a is None:
+            return None
+        return callback_sources((("t_eq", 0, 0.0), a), dtype)[1]
+    affect = aff(cc.get("affect"))
+    neg = cc.get("affect_neg", "same")
+    kw = dict(affect_neg="same" if neg == "same" else aff(neg), rootfind=cc.get("rootfind", "left"))
+    for k in ("abstol", "repeat_nudge", "dtrelax"):
+        if k in cc:
+            kw[k] = cc[k]
+    return cond, affect, kw

@@ -12,7 +12,7 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(Path(__file__).resolve().parent))
-from cases import P0_LORENZ, U0_LORENZ, callback_sources, lorenz_sweep  # noqa: E402
+from cases import P0_LORENZ, U0_LORENZ, callback_sources, continuous_callback_sources, lorenz_sweep  # noqa: E402
 
 f32, f64 = np.float32, np.float64
 KICK = (("t_eq", 0, 2.4), ("u_add", 0, 10.0))          # condition(u,t,integ) = t == 2.4f0; affect!: u += 10
@@ -135,8 +135,8 @@ def test_callback_argument_checks():
     import diffeqgpu_b200 as dg
     with pytest.raises(ValueError, match="save_positions"):
         dg.DiscreteCallback("return true;", "", save_positions=(True, True))       # callbacks.jl:12-14
-    with pytest.raises(NotImplementedError):
-        dg.ContinuousCallback("return u[0];", "")
+    with pytest.raises(ValueError, match="save_positions"):
+        dg.ContinuousCallback("return u[0];", "u[1] = -u[1];", save_positions=(True, False))
     cs = dg.CallbackSet(dg.DiscreteCallback("return true;", "u[0] = 0;"), None,
                         dg.CallbackSet(dg.DiscreteCallback("return false;", "")))
     assert len(cs) == 2
@@ -333,3 +333,120 @@ def test_gpu_stiff_events_bit_exact(oracle, alg):
     g["_t0"] = 0.0
     assert (g["retcode"] == 6).any()
     assert_same(g, r, f"rober terminate {alg}", written_only=True)
+
+
+# ------------------------------------------------------------------------------------------
+# continuous callbacks: the bouncing ball of test/gpu_kernel_de/gpu_ode_continuous_callbacks.jl
+# (x'' = -10, x0 = 45, perfectly elastic bounce: u[2] = -u[2] when x crosses 0 from above; the exact
+# flight is x = 45 - 5 t^2 until t = 3, then parabolas of period 6)
+# ------------------------------------------------------------------------------------------
+BOUNCE = dict(condition=("u_minus", 0, 0.0), affect=("u_scale", 1, -1.0))
+
+
+def exact_ball(t):
+    if t < 3:
+        return np.array([45 - 5 * t * t, -10 * t])
+    s = (t - 3) % 6
+    return np.array([30 * s - 5 * s * s, 30 - 10 * s])
+
+
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "vern9"])
+def test_oracle_bouncing_ball(oracle, alg):
+    kw = dict(continuous_callbacks=[BOUNCE])
+    # "Unadaptive version": dt = 0.1, every-step saves; the last written row is at tf
+    r = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 15], dt=0.1, length=160, **kw)
+    ts, us = r["ts"][0], r["us"][0]
+    last = np.nonzero(ts != 0)[0][-1]
+    assert ts[last] == f32(15.0) and abs(us[last, 0]) < 2e-3 and abs(abs(us[last, 1]) - 30) < 2e-3
+    # saveat = [0, 9.1] with dt = 1 (:66-80): second bounce at t = 9
+    r = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 10], dt=1.0, saveat=np.array([0.0, 9.1], f32), **kw)
+    # (the reference runs this test with Tsit5 and Vern7 only: in Float32 the Vern9 dense output, whose
+    #  polynomial coefficients reach 1e4 with alternating signs, loses ~2 digits at dt = 1)
+    assert np.linalg.norm(r["us"][0, 1] - exact_ball(9.1)) < (2e-3 if alg != "vern9" else 0.1)
+    # save_everystep = false
+    r = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 14], dt=0.1, save_everystep=False, **kw)
+    assert np.linalg.norm(r["us"][0, 1] - exact_ball(float(r["ts"][0, 1]))) < 2e-3
+    # adaptive (:104-118, tolerance 1e-2 there)
+    r = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 14], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-3,
+                     save_everystep=False, **kw)
+    assert r["ts"][0, 1] == f32(14.0) and np.linalg.norm(r["us"][0, 1] - exact_ball(14.0)) < 1e-2
+    # CallbackSet(cb, cb): same result (the first callback's affect runs, once per event)
+    r2 = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 14], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-3,
+                      save_everystep=False, continuous_callbacks=[BOUNCE, BOUNCE])
+    assert np.array_equal(r["us"], r2["us"])
+    # terminate! at the first impact: ReturnCode.Terminated at t = 3
+    stop = dict(condition=("u_minus", 0, 0.0), affect=("terminate", 0, 0.0))
+    r = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 14], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6,
+                     save_everystep=False, continuous_callbacks=[stop])
+    assert r["retcode"][0] == 6 and abs(r["ts"][0, 1] - 3.0) < 1e-4 and abs(r["us"][0, 1, 1] + 30) < 1e-3
+
+
+def gpu_cc(dg, alg, u0, p, tspan, ccs, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3, saveat=None, save_everystep=True,
+           fp_mode="strict"):
+    import torch
+    u0 = np.asarray(u0, f32); p = np.asarray(p, f32)
+    prob = dg.ODEProblem(dg.models.ball_src, u0[0] if u0.ndim == 2 else u0, tuple(tspan), p[0] if p.ndim == 2 else p)
+    n = max(u0.shape[0] if u0.ndim == 2 else 1, p.shape[0] if p.ndim == 2 else 1)
+    probs = dg.ProblemBatch.from_arrays(prob, u0=u0 if u0.ndim == 2 else None, p=p if p.ndim == 2 else None, n_traj=n, device="cuda:0")
+    cbs = []
+    for cc in ccs:
+        cond, aff, kw = continuous_callback_sources(cc)
+        cbs.append(dg.ContinuousCallback(cond, aff, **kw))
+    cb = dg.CallbackSet(*cbs)
+    a = getattr(dg, ALGS[alg])()
+    kw = dict(dt=f32(dt), saveat=saveat, save_everystep=save_everystep, callback=cb, fp_mode=fp_mode, stats=True)
+    if adaptive:
+        ts, us, st = dg.vectorized_asolve(probs, prob, a, abstol=f32(abstol), reltol=f32(reltol), **kw)
+    else:
+        ts, us, st = dg.vectorized_solve(probs, prob, a, **kw)
+    torch.cuda.synchronize()
+    return dict(ts=ts.cpu().numpy(), us=us.cpu().numpy(), naccept=st["naccept"].cpu().numpy(),
+                nreject=st["nreject"].cpu().numpy(), retcode=st["retcode"].cpu().numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "vern9"])
+def test_gpu_bouncing_ball_bit_exact(oracle, alg):
+    import diffeqgpu_b200 as dg
+    n = 200
+    rng = np.random.default_rng(5)
+    u0 = np.stack([rng.uniform(20, 60, n), rng.uniform(-5, 5, n)], 1).astype(f32)
+    p = rng.uniform(5, 15, (n, 1)).astype(f32)
+    ccs = [BOUNCE]
+    for kw in (dict(dt=0.1), dict(dt=0.1, save_everystep=False), dict(dt=1.0, saveat=np.array([0.0, 4.3, 9.1], f32))):
+        g = gpu_cc(dg, alg, u0, p, [0, 10], ccs, **kw)
+        okw = dict(kw)
+        if "saveat" not in kw and kw.get("save_everystep", True):
+            okw["length"] = g["us"].shape[1]
+        r = oracle.solve("ball", alg, u0, p, [0, 10], continuous_callbacks=ccs, **okw)
+        w = np.ones(g["ts"].shape, bool)
+        w[:, 1:] = g["ts"][:, 1:] != 0                  # rows the shifted time grid never reached are uninitialised
+        assert np.array_equal(g["ts"], r["ts"]) and np.array_equal(g["us"][w], r["us"][w]), sorted(kw)
+        assert np.array_equal(g["naccept"], r["naccept"])
+    akw = dict(dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-4)
+    for kw in (dict(save_everystep=False), dict(saveat=np.arange(0, 11, dtype=f32))):
+        g = gpu_cc(dg, alg, u0, p, [0, 10], ccs, **akw, **kw)
+        r = oracle.solve("ball", alg, u0, p, [0, 10], continuous_callbacks=ccs, **akw, **kw)
+        assert_same(g, r, f"adaptive ball {alg} {sorted(kw)}")
+        assert (g["us"][:, -1, 0] > -1e-3).all()       # the ball never ends below the floor
+    # terminate! at the first impact + a discrete callback in the same set
+    stop = dict(condition=("u_minus", 0, 0.0), affect=("terminate", 0, 0.0), rootfind="right")
+    g = gpu_cc(dg, alg, u0, p, [0, 10], [stop], save_everystep=False, **akw)
+    r = oracle.solve("ball", alg, u0, p, [0, 10], continuous_callbacks=[stop], save_everystep=False, **akw)
+    assert_same(g, r, f"terminate ball {alg}")
+    assert (g["retcode"] == 6).all() and (np.abs(g["us"][:, 1, 0]) < 1e-2).all()
+
+
+@pytest.mark.gpu
+def test_gpu_high_level_bouncing_ball():
+    """gpu_ode_continuous_callbacks.jl:30-60 through solve(EnsembleProblem, ...; callback = ContinuousCallback(...))"""
+    import diffeqgpu_b200 as dg
+    prob = dg.ODEProblem(dg.models.ball_src, np.array([45.0, 0.0], f32), (0.0, 15.0), np.array([10.0], f32))
+    monteprob = dg.EnsembleProblem(prob, safetycopy=False)
+    cb = dg.ContinuousCallback("return u[0];", "u[1] = u[1] + (T)-2 * u[1];")       # integrator.u += [0, -2] .* integrator.u
+    for alg in (dg.GPUTsit5(), dg.GPUVern7()):
+        sol = dg.solve(monteprob, alg, dg.EnsembleGPUKernel(), trajectories=2, adaptive=False, dt=f32(0.1), callback=cb, merge_callbacks=True)
+        assert abs(sol[0].u[-1, 0]) < 2e-3 and abs(abs(sol[0].u[-1, 1]) - 30) < 2e-3
+        sol = dg.solve(monteprob, alg, dg.EnsembleGPUKernel(), trajectories=2, adaptive=True, dt=f32(0.1), callback=dg.CallbackSet(cb, cb),
+                       merge_callbacks=True, saveat=np.array([0.0, 9.1], f32))
+        assert np.linalg.norm(sol[1].u[-1] - exact_ball(9.1)) < 1e-2

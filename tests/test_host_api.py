@@ -62,9 +62,9 @@ def test_error_behaviour_matches_reference():
         dg.vectorized_solve(None, nd, dg.GPUSIEA(), dt=0.1)
     with pytest.raises(TypeError):
         dg.vectorized_solve(None, lorenz_prob(), dg.GPUEM(), dt=0.1)
-    # tstops / discrete callbacks are lowered (tests/test_events.py); continuous callbacks are not
-    with pytest.raises(NotImplementedError):
-        dg.ContinuousCallback("return u[0];", "u[0] = 0;")
+    # tstops, discrete and continuous callbacks are lowered (tests/test_events.py); save_positions must be (false, false)
+    with pytest.raises(ValueError, match="save_positions"):
+        dg.ContinuousCallback("return u[0];", "u[0] = 0;", save_positions=(True, True))
 
 
 def test_solving_without_gpu_fails_loudly():
