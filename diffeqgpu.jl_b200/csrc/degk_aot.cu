@@ -23,6 +23,9 @@
 #include "device/degk_sde_kernels.cuh"
 #include "degk_internal.h"
 
+#ifndef DEGK_A2_MINBLOCKS_F64
+#define DEGK_A2_MINBLOCKS_F64 1   // Float64: no register cap (Vern9 needs 234); 3 blocks/SM (168 registers) spills ~500 B
+#endif
 #ifndef DEGK_A2_MINBLOCKS
 #define DEGK_A2_MINBLOCKS 4   // resident blocks per SM the Float32 adaptive kernel is compiled for (register cap 128)
 #endif
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(DEGK_BLOCK) k_ode_asolve(const KArgs a) {
 template <int FPMODE, class T, class Model, template <class, class> class Method, int W>
 // Float32: cap at 128 registers (4 blocks of 128 threads per SM).  Forcing 5 blocks (96 registers)
 // was measured slower on C2 (85 vs 92 G steps/s: the spills cost more than the extra warps hide).
-__global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? DEGK_A2_MINBLOCKS : 1)) k_ode_asolve2(const KArgs a) {
+__global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? DEGK_A2_MINBLOCKS : DEGK_A2_MINBLOCKS_F64)) k_ode_asolve2(const KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
     ode_asolve_gen_body<T, Model, Method, W>(a, degk_smem);
 }
