@@ -299,6 +299,8 @@ def main():
     # ---- CPU baseline (oracle port, bounded sample) ----
     cpu = None
     try:
+        if world > 1:
+            raise RuntimeError("measured at N = 1 only (the other ranks' host threads share the cores)")
         from oracle import oracle
         cores = os.cpu_count() or 1
         ps = (np.random.default_rng(0).random((args.cpu_traj, 3), dtype=np.float32) * P0)
