@@ -248,13 +248,24 @@ struct Rodas {
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
                                  T (&unew)[N], T (&err)[N]) {
-        static_assert(!has_mass_of<Model>::value, "mass matrices are lowered for GPURosenbrock23 only");
         T J[N][N], dT[N];
         eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
         eval_tgrad<T, Model>(dT, uprev, p, t);
         const T dtgamma = h * RC(gamma);
         const T invdg = (T)1 / dtgamma;
-        DEGK_UNROLL for (int i = 0; i < N; ++i) J[i][i] = J[i][i] - invdg;    // W = J - I/(dt*gamma)
+        // W = J - mass_matrix * inv(dtgamma) (gpu_rodas5P_perform_step.jl:81-82, 238-239); every
+        // `mass_matrix * (dtC.. * k..)` below goes through MASSV (identity: nothing happens)
+        constexpr bool MASS = has_mass_of<Model>::value;
+        T Mm[MASS ? N : 1][MASS ? N : 1];
+        if constexpr (MASS) {
+            Model::template mass<T>(Mm);
+            DEGK_UNROLL for (int i = 0; i < N; ++i)
+                DEGK_UNROLL for (int j = 0; j < N; ++j) J[i][j] = J[i][j] - Mm[i][j] * invdg;
+        } else {
+            DEGK_UNROLL for (int i = 0; i < N; ++i) J[i][i] = J[i][i] - invdg;
+        }
+#define MASSV(v) do { if constexpr (MASS) { T mv_[N]; mass_mul<T, N>(Mm, v, mv_); DEGK_UNROLL for (int c_ = 0; c_ < N; ++c_) v[c_] = mv_[c_]; } } while (0)
+        T cs[N];
         LinSolve<T, N> F;
         if (!F.factor(J)) return false;
         T (&k)[NS][N] = K.ks;
@@ -268,22 +279,26 @@ struct Rodas {
         Model::template f<T>(du, uu, p, t + RC(c2) * h);
         // Step 2
         { const T dtd2 = h * RC(d2), C21 = RC(C21) / h;
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd2 * dT[c]) + C21 * k[0][c]); }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = C21 * k[0][c];
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd2 * dT[c]) + cs[c]); }
         F.solve(lt, k[1]);
         DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = (uprev[c] + RC(a31) * k[0][c]) + RC(a32) * k[1][c];
         Model::template f<T>(du, uu, p, t + RC(c3) * h);
         // Step 3
         { const T dtd3 = h * RC(d3), C31 = RC(C31) / h, C32 = RC(C32) / h;
-          DEGK_UNROLL for (int c = 0; c < N; ++c)
-              lt[c] = -((du[c] + dtd3 * dT[c]) + (C31 * k[0][c] + C32 * k[1][c])); }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (C31 * k[0][c] + C32 * k[1][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd3 * dT[c]) + cs[c]); }
         F.solve(lt, k[2]);
         DEGK_UNROLL for (int c = 0; c < N; ++c)
             uu[c] = ((uprev[c] + RC(a41) * k[0][c]) + RC(a42) * k[1][c]) + RC(a43) * k[2][c];
         Model::template f<T>(du, uu, p, t + RC(c4) * h);
         // Step 4
         { const T dtd4 = h * RC(d4), C41 = RC(C41) / h, C42 = RC(C42) / h, C43 = RC(C43) / h;
-          DEGK_UNROLL for (int c = 0; c < N; ++c)
-              lt[c] = -((du[c] + dtd4 * dT[c]) + ((C41 * k[0][c] + C42 * k[1][c]) + C43 * k[2][c])); }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((C41 * k[0][c] + C42 * k[1][c]) + C43 * k[2][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd4 * dT[c]) + cs[c]); }
         F.solve(lt, k[3]);
         DEGK_UNROLL for (int c = 0; c < N; ++c)
             uu[c] = (((uprev[c] + RC(a51) * k[0][c]) + RC(a52) * k[1][c]) + RC(a53) * k[2][c]) + RC(a54) * k[3][c];
@@ -292,9 +307,9 @@ struct Rodas {
             Model::template f<T>(du, uu, p, t + R5C(c5) * h);
             // Step 5: summands in the order k2,k4,k1,k3 (gpu_rodas5P_perform_step.jl:271)
             { const T dtd5 = h * R5C(d5);
-              DEGK_UNROLL for (int c = 0; c < N; ++c)
-                  lt[c] = -((du[c] + dtd5 * dT[c]) +
-                            (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c])); }
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd5 * dT[c]) + cs[c]); }
             F.solve(lt, k[4]);
             DEGK_UNROLL for (int c = 0; c < N; ++c)
                 uu[c] = ((((uprev[c] + R5C(a61) * k[0][c]) + R5C(a62) * k[1][c]) + R5C(a63) * k[2][c]) +
@@ -302,46 +317,52 @@ struct Rodas {
             Model::template f<T>(du, uu, p, t + h);
             // Step 6
             { const T C61 = R5C(C61) / h, C62 = R5C(C62) / h, C63 = R5C(C63) / h, C64 = R5C(C64) / h, C65 = R5C(C65) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c)
-                  lt[c] = -(du[c] + ((((C61 * k[0][c] + C62 * k[1][c]) + C63 * k[2][c]) + C64 * k[3][c]) + C65 * k[4][c])); }
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((C61 * k[0][c] + C62 * k[1][c]) + C63 * k[2][c]) + C64 * k[3][c]) + C65 * k[4][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
             F.solve(lt, k[5]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[5][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 7
             { const T C71 = R5C(C71) / h, C72 = R5C(C72) / h, C73 = R5C(C73) / h, C74 = R5C(C74) / h,
                       C75 = R5C(C75) / h, C76 = R5C(C76) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c)
-                  lt[c] = -(du[c] + (((((C71 * k[0][c] + C72 * k[1][c]) + C73 * k[2][c]) + C74 * k[3][c]) +
-                                      C75 * k[4][c]) + C76 * k[5][c])); }
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((((C71 * k[0][c] + C72 * k[1][c]) + C73 * k[2][c]) + C74 * k[3][c]) +
+                                      C75 * k[4][c]) + C76 * k[5][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
             F.solve(lt, k[NS > 6 ? 6 : 0]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[NS > 6 ? 6 : 0][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 8
             { const T C81 = R5C(C81) / h, C82 = R5C(C82) / h, C83 = R5C(C83) / h, C84 = R5C(C84) / h,
                       C85 = R5C(C85) / h, C86 = R5C(C86) / h, C87 = R5C(C87) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c)
-                  lt[c] = -(du[c] + ((((((C81 * k[0][c] + C82 * k[1][c]) + C83 * k[2][c]) + C84 * k[3][c]) +
-                                       C85 * k[4][c]) + C86 * k[5][c]) + C87 * k[NS > 6 ? 6 : 0][c])); }
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((((C81 * k[0][c] + C82 * k[1][c]) + C83 * k[2][c]) + C84 * k[3][c]) +
+                                       C85 * k[4][c]) + C86 * k[5][c]) + C87 * k[NS > 6 ? 6 : 0][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
             F.solve(lt, k[NS - 1]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uu[c] + k[NS - 1][c];
         } else {
             Model::template f<T>(du, uu, p, t + h);
             // Step 5: summands in the order k2,k4,k1,k3 (gpu_rodas4_perform_step.jl:213)
-            DEGK_UNROLL for (int c = 0; c < N; ++c)
-                lt[c] = -(du[c] + (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]));
+            DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]);
             F.solve(lt, k[4]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[4][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 6: summands in the order k1,k2,k5,k4,k3 (:219)
             { const T C61 = R4C(C61) / h, C62 = R4C(C62) / h, C63 = R4C(C63) / h, C64 = R4C(C64) / h, C65 = R4C(C65) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c)
-                  lt[c] = -(du[c] + ((((C61 * k[0][c] + C62 * k[1][c]) + C65 * k[4][c]) + C64 * k[3][c]) + C63 * k[2][c])); }
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((C61 * k[0][c] + C62 * k[1][c]) + C65 * k[4][c]) + C64 * k[3][c]) + C63 * k[2][c]);
+          MASSV(cs);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
             F.solve(lt, k[5]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uu[c] + k[5][c];
         }
         if (WANT_ERR) {
             DEGK_UNROLL for (int c = 0; c < N; ++c) err[c] = k[NS - 1][c];
         }
+#undef MASSV
         return true;
     }
 

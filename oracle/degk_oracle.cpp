@@ -893,7 +893,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
     for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
     if ((a.n_tstops > 0 || a.n_cb > 0 || a.n_cc > 0) && (a.alg == A_EM || a.alg == A_SIEA || a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -3;   // events: RK / Rosenbrock steppers
     if (saveat && (a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -4;   // no dense output in the reference
-    if (a.model == M_ROBER_DAE && a.alg != A_ROS23) return -5;              // mass matrices: Rosenbrock23 only
+    if (a.model == M_ROBER_DAE && a.alg != A_ROS23 && a.alg != A_RODAS4 && a.alg != A_RODAS5P) return -5;   // mass matrices: Rosenbrock family
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < a.n_traj; ++i) {
         const T* ui = u0 + i * a.u0_stride;

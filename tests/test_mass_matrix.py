@@ -1,5 +1,6 @@
-"""Constant mass matrix M u' = f(u, p, t) with GPURosenbrock23: Robertson in DAE
-form, M = diag(1, 1, 0), as in test/gpu_kernel_de/stiff_ode/gpu_ode_mass_matrix.jl."""
+"""Constant mass matrix M u' = f(u, p, t) with the Rosenbrock family: Robertson in DAE
+form, M = diag(1, 1, 0), as in test/gpu_kernel_de/stiff_ode/gpu_ode_mass_matrix.jl (GPURosenbrock23 there;
+GPURodas4 / GPURodas5P carry the same `mass_matrix - gamma*J` W and `mass_matrix * (C-sum)` terms)."""
 import sys
 from pathlib import Path
 
@@ -41,9 +42,30 @@ def test_oracle_robertson_dae(oracle):
     a = oracle.solve("rober_dae", "rosenbrock23", [1, 0, 0], k, [0, 1e3], dt=0.1, adaptive=True, abstol=1e-5, reltol=1e-5, save_everystep=False)
     b = oracle.solve("rober_dae", "rosenbrock23", [1, 0, 0], k, [0, 1e3], dt=0.1, adaptive=True, abstol=1e-5, reltol=1e-5, save_everystep=False, jac_mode=2)
     assert np.array_equal(a["us"], b["us"])
-    # other solvers: not lowered
-    with pytest.raises(RuntimeError):
-        oracle.solve("rober_dae", "rodas5p", [1, 0, 0], k, [0, 1.0], dt=0.1, adaptive=True, save_everystep=False)
+    # other solver families: not lowered
+    for alg in ("tsit5", "kvaerno3"):
+        with pytest.raises(RuntimeError):
+            oracle.solve("rober_dae", alg, [1, 0, 0], k, [0, 1.0], dt=0.1, adaptive=True, save_everystep=False)
+
+
+@pytest.mark.parametrize("alg", ["rodas4", "rodas5p"])
+def test_oracle_robertson_dae_rodas(oracle, alg):
+    # Float64, tight tolerance: the DAE form lands on the literature value and holds the constraint to rounding;
+    # it differs from the ODE form only at rounding level (same steps), which shows the mass terms are exercised
+    kw = dict(dt=1e-4, adaptive=True, abstol=1e-9, reltol=1e-8, save_everystep=False, dtype=f64)
+    r = oracle.solve("rober_dae", alg, [1, 0, 0], K0[None], [0, 1e5], **kw)
+    o = oracle.solve("rober", alg, [1, 0, 0], K0[None], [0, 1e5], **kw)
+    assert r["retcode"][0] == 1 and np.allclose(r["us"][0, 1], REF_END, rtol=2e-5)
+    assert abs(r["us"][0, 1].sum() - 1) < 1e-14
+    assert np.allclose(r["us"][0, 1], o["us"][0, 1], rtol=1e-7) and not np.array_equal(r["us"][0, 1], o["us"][0, 1])
+    # Float32 at the reference test's tolerances
+    r = oracle.solve("rober_dae", alg, [1, 0, 0], K0[None].astype(f32), [0, 1e5], dt=1e-4, adaptive=True, abstol=1e-8, reltol=1e-4,
+                     save_everystep=False)
+    assert r["retcode"][0] == 1 and np.linalg.norm(r["us"][0, 1] - REF_END) < 8e-4 and abs(r["us"][0, 1].sum() - 1) < 1e-5
+    # analytic Jacobian and duals agree bit for bit
+    b = oracle.solve("rober_dae", alg, [1, 0, 0], K0[None].astype(f32), [0, 1e5], dt=1e-4, adaptive=True, abstol=1e-8, reltol=1e-4,
+                     save_everystep=False, jac_mode=2)
+    assert np.array_equal(r["us"], b["us"])
 
 
 def test_mass_matrix_lowering_compiles():
@@ -55,9 +77,18 @@ def test_mass_matrix_lowering_compiles():
                                dtype=dt, alg=3, fp_mode=fp)       # no jac body: forward-mode duals
             st, nb, log = _lib.jit_compile_check(d)
             assert st == 0 and nb > 0, log
-    st, _, log = _lib.jit_compile_check(_lib.make_desc(rhs_src=dg.models.ROBER_DAE_RHS, mass_src="Mm[0][0] = (T)1;", n_state=3,
-                                                       n_param=3, dtype=_lib.F32, alg=5))
-    assert st == _lib.ERR_UNSUPPORTED and "GPURosenbrock23 only" in log
+    for alg in (4, 5):                                            # GPURodas4 / GPURodas5P
+        for fp in (_lib.FP_STRICT, _lib.FP_FAST):
+            d = _lib.make_desc(rhs_src=dg.models.ROBER_DAE_RHS, jac_src=dg.models.ROBER_DAE_JAC, mass_src="Mm[0][0] = (T)1; Mm[1][1] = (T)1;",
+                               n_state=3, n_param=3, dtype=_lib.F32, alg=alg, fp_mode=fp)
+            st, nb, log = _lib.jit_compile_check(d)
+            assert st == 0 and nb > 0, log
+    for alg in (0, 8):                                            # GPUTsit5, GPUKvaerno3: refused, user bodies and built-in
+        st, _, log = _lib.jit_compile_check(_lib.make_desc(rhs_src=dg.models.ROBER_DAE_RHS, mass_src="Mm[0][0] = (T)1;", n_state=3,
+                                                           n_param=3, dtype=_lib.F32, alg=alg))
+        assert st == _lib.ERR_UNSUPPORTED and "Rosenbrock family only" in log
+        st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="rober_dae", dtype=_lib.F32, alg=alg, force_jit=True))
+        assert st == _lib.ERR_UNSUPPORTED and "Rosenbrock family only" in log
 
 
 @pytest.mark.gpu
@@ -100,3 +131,40 @@ def test_gpu_robertson_dae_bit_exact(oracle):
     both = good & gf_good
     assert both.mean() > 0.9 and np.abs(gf["us"][both] - g["us"][both]).max() < 2e-3
     assert np.isin(gf["retcode"], (1, 2, 3)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["rodas4", "rodas5p"])
+def test_gpu_robertson_dae_rodas_bit_exact(oracle, alg):
+    import torch
+    import diffeqgpu_b200 as dg
+    k = (K0 * (0.5 + np.random.default_rng(5).random((200, 3)))).astype(f32)
+    sv = np.array([1.0, 1e2, 1e3, 1e4], f32)
+    Alg = dict(rodas4=dg.GPURodas4, rodas5p=dg.GPURodas5P)[alg]
+
+    def gpu(func, fp_mode="strict", **kw):
+        prob = dg.ODEProblem(func, np.array([1, 0, 0], f32), (0.0, 1e4), k[0])
+        probs = dg.ProblemBatch.from_arrays(prob, p=k, device="cuda:0")
+        ts, us, st = dg.vectorized_asolve(probs, prob, Alg(), dt=f32(1e-4), abstol=f32(1e-8), reltol=f32(1e-4),
+                                          fp_mode=fp_mode, stats=True, **kw)
+        torch.cuda.synchronize()
+        return dict(ts=ts.cpu().numpy(), us=us.cpu().numpy(), naccept=st["naccept"].cpu().numpy(),
+                    nreject=st["nreject"].cpu().numpy(), retcode=st["retcode"].cpu().numpy())
+
+    okw = dict(dt=1e-4, adaptive=True, abstol=1e-8, reltol=1e-4)
+    for kw in (dict(save_everystep=False), dict(saveat=sv)):
+        r = oracle.solve("rober_dae", alg, [1, 0, 0], k, [0, 1e4], **okw, **kw)
+        for func in (dg.models.rober_dae, dg.models.rober_dae_src):          # built-in struct and user bodies
+            g = gpu(func, **kw)
+            for key in ("ts", "naccept", "nreject", "retcode"):
+                assert np.array_equal(g[key], r[key], equal_nan=True), (key, sorted(kw))
+            w = g["ts"] != 0
+            w[:, 0] = True if "saveat" not in kw else w[:, 0]
+            assert np.array_equal(g["us"][w], r["us"][w], equal_nan=True), ("us", sorted(kw))
+    ok = g["retcode"] == 1
+    assert ok.mean() > 0.95 and np.abs(g["us"][ok].sum(axis=2) - 1).max() < 1e-4
+    # fast build (packed pairs): same solution within tolerance
+    gf = gpu(dg.models.rober_dae, fp_mode="fast", saveat=sv)
+    both = ok & (gf["retcode"] == 1)
+    assert both.mean() > 0.9 and np.abs(gf["us"][both] - g["us"][both]).max() < 2e-3
+    assert np.abs(gf["us"][both].sum(axis=2) - 1).max() < 1e-4
