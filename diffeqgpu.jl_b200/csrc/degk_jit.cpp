@@ -314,10 +314,6 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
             degk_set_error(ctx, "n_ccallbacks must be in 0..8 with condition sources");
             return DEGK_ERR_INVALID;
         }
-        if (d->n_ccallbacks > 0 && stiff) {
-            degk_set_error(ctx, "continuous callbacks are lowered for the explicit RK solvers");
-            return DEGK_ERR_UNSUPPORTED;
-        }
         snprintf(buf, sizeof buf, "    static constexpr int NCC = %d;\n", d->n_ccallbacks);
         src += buf;
         for (int c = 0; c < d->n_ccallbacks; ++c) {

@@ -75,6 +75,9 @@ rober_dae_src = ODEFunction(rhs=ROBER_DAE_RHS, jac=ROBER_DAE_JAC, mass_matrix=" 
 # bouncing ball x'' = -g: test/gpu_kernel_de/gpu_ode_continuous_callbacks.jl:6-10
 BALL_RHS = "    du[0] = u[1];\n    du[1] = -p[0];\n"
 ball_src = ODEFunction(rhs=BALL_RHS, n_state=2, n_param=1, python=lambda u, p, t: np.array([u[1], -p[0]]))
+# with the analytic jac / tgrad of test/gpu_kernel_de/stiff_ode/gpu_ode_continuous_callbacks.jl:11-21
+ball_jac_src = ODEFunction(rhs=BALL_RHS, jac="    J[0][1] = (T)1;\n", tgrad="", n_state=2, n_param=1,
+                           python=lambda u, p, t: np.array([u[1], -p[0]]))
 
 # test/gpu_kernel_de/finite_diff.jl:6-9 / forward_diff.jl: du = -p u^2, NO analytic Jacobian: the stiff
 # solvers differentiate it (forward-mode duals, or finite differences with autodiff = False)
