@@ -26,6 +26,14 @@ class DiscreteCallback:
             raise TypeError("condition and affect must be CUDA-C function bodies (str)")
         self.condition, self.affect = condition, affect
 
+    @classmethod
+    def from_python(cls, condition, affect, n_state, n_param=0, **kw):
+        """condition(u, t, p) -> comparison, affect(u, p, t) -> new u | (new u, new p) | 'terminate': host
+        functions traced once and lowered to the bodies above (lowering.py)"""
+        from . import lowering
+        return cls(lowering.lower_condition(condition, n_state, n_param),
+                   lowering.lower_affect(affect, n_state, n_param), **kw)
+
 
 GPUDiscreteCallback = DiscreteCallback
 
@@ -56,6 +64,15 @@ class ContinuousCallback:
     def key(self):
         return (self.condition, self.affect, self.affect_neg, self.ROOTFIND[self.rootfind], self.abstol, self.repeat_nudge,
                 self.dtrelax)
+
+    @classmethod
+    def from_python(cls, condition, affect, n_state, n_param=0, *, affect_neg="same", **kw):
+        """condition(u, t, p) -> value of the root function, affect / affect_neg as DiscreteCallback.from_python
+        (None = `nothing`)"""
+        from . import lowering
+        low = lambda a: None if a is None else lowering.lower_affect(a, n_state, n_param)   # noqa: E731
+        return cls(lowering.lower_condition(condition, n_state, n_param, continuous=True), low(affect),
+                   affect_neg="same" if isinstance(affect_neg, str) and affect_neg == "same" else low(affect_neg), **kw)
 
 
 GPUContinuousCallback = ContinuousCallback

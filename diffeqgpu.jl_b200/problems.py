@@ -45,6 +45,26 @@ class ODEFunction:
         if self.builtin is None and self.n_state <= 0:
             raise ValueError("n_state is required for a source-defined ODEFunction")
 
+    @classmethod
+    def from_python(cls, f, n_state, n_param=0, *, jac=False, mass_matrix=None):
+        """Lower a host function f(u, p, t) -> du to CUDA C++ bodies by tracing it once (lowering.py; the role of
+        Symbolics `build_function(target = CTarget())` / ModelingToolkit in docs/src/tutorials/modelingtoolkit.md).
+        `jac=True` also derives the analytic Jacobian and time gradient symbolically (`ODEFunction(f; jac, tgrad)`).
+        `mass_matrix`: constant n x n array (zeros are skipped), as `ODEFunction(f; mass_matrix = M)`."""
+        from . import lowering
+        src = lowering.lower_function(f, n_state, n_param, jac=jac)
+        mm = None
+        if mass_matrix is not None:
+            M = np.asarray(mass_matrix, dtype=np.float64)
+            if M.shape != (n_state, n_state):
+                raise ValueError(f"mass_matrix must be {n_state} x {n_state}")
+            mm = "".join(f"    Mm[{i}][{j}] = (T){float(M[i, j])!r};\n" for i in range(n_state) for j in range(n_state) if M[i, j] != 0)
+
+        def host(u, p, t):
+            return np.asarray(f(list(u), list(p), t), dtype=np.float64)
+        return cls(rhs=src["rhs"], jac=src["jac"], tgrad=src["tgrad"], n_state=n_state, n_param=n_param, python=host,
+                   mass_matrix=mm)
+
 
 @dataclass(frozen=True)
 class SDEFunction:
@@ -53,6 +73,17 @@ class SDEFunction:
     g: Optional[str] = None
     noise: str = "diagonal"
     n_noise: int = 0
+
+    @classmethod
+    def from_python(cls, f, g, n_state, n_param=0, *, noise="diagonal", n_noise=0):
+        """Lower drift f(u, p, t) and diffusion g(u, p, t) (a vector for diagonal noise, an n x m matrix with
+        `noise="general"`, the reference's `noise_rate_prototype`) to CUDA C++ bodies (lowering.py)."""
+        from . import lowering
+        if noise not in ("diagonal", "general"):
+            raise ValueError("noise must be 'diagonal' or 'general'")
+        body = lowering.lower_noise(g, n_state, n_param, noise=noise, n_noise=n_noise)
+        return cls(ODEFunction.from_python(f, n_state, n_param), g=body, noise=noise,
+                   n_noise=n_noise if noise == "general" else 0)
 
 
 BUILTIN_DIMS = {  # name -> (n_state, n_param, n_noise, noise_kind); mirror of degk_models.cuh
