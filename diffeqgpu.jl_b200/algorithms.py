@@ -65,7 +65,7 @@ class GPURodas5P(GPUODEImplicitAlgorithm):
 
 
 class GPUKvaerno3(GPUODEImplicitAlgorithm):
-    """ESDIRK + Newton (gpu_kvaerno3_perform_step.jl); no dense output in the reference: no saveat"""
+    """ESDIRK + Newton (gpu_kvaerno3_perform_step.jl); saveat through the default Hermite interpolant"""
     alg_id, order = 8, 3
 
 

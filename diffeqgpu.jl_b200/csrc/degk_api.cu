@@ -350,11 +350,6 @@ static int validate(degk_program* prog, const degk_solve_args* a) {
         return DEGK_ERR_INVALID;
     }
     if (a->out_layout != DEGK_LAYOUT_REF && a->out_layout != DEGK_LAYOUT_SOA) { degk_set_error(ctx, "bad out_layout"); return DEGK_ERR_INVALID; }
-    if (a->saveat && (prog->info.alg == DEGK_ALG_KVAERNO3 || prog->info.alg == DEGK_ALG_KVAERNO5)) {
-        // the reference has no _ode_interpolant method for the Kvaerno integrators: saveat would raise there
-        degk_set_error(ctx, "GPUKvaerno3/5 have no dense output: saveat is not available (use save_everystep or endpoints)");
-        return DEGK_ERR_UNSUPPORTED;
-    }
     if (a->tstops && a->n_tstops > 0 && !prog->has_events) {
         degk_set_error(ctx, "tstops need a program built with degk_model_desc.events = 1");
         return DEGK_ERR_UNSUPPORTED;

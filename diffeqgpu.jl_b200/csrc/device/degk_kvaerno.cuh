@@ -170,7 +170,8 @@ struct Kvaerno {
             LinSolve<T, N> F;
             if (!F.factor(W)) return false;
             F.solve(b, err);
-            DEGK_UNROLL for (int c = 0; c < N; ++c) K.k1[c] = k1[c];       // integ.k1 = k1 on accept (kept for interp)
+            // integ.k1 = k1 on accept: the slope the interpolant sees (k1next) is the one at uprev
+            DEGK_UNROLL for (int c = 0; c < N; ++c) { K.k1[c] = k1[c]; K.k1next[c] = k1[c]; }
         } else {
             // integ.k1 = f(integ.u, p, t) with t the time captured before the step (:78-81)
             Model::template f<T>(K.k1next, unew, p, t);
@@ -178,17 +179,27 @@ struct Kvaerno {
         return true;
     }
 
-    // cubic Hermite through (uprev, k1) and (unew, k2): extension, the reference has no interpolant here
+    // The integrators without an `_ode_interpolant` method of their own fall to the default Hermite one
+    // (nonstiff/interpolants.jl:1-21, `@muladd`), evaluated with whatever integ.k1 / integ.k2 hold when
+    // savevalues! runs: adaptive k1 = f(uprev, p, t), fixed dt k1 = f(u_new, p, t_old) (the FSAL value stored
+    // at the end of the step, gpu_kvaerno3_perform_step.jl:78-81) -- K.k1next in both cases -- and k2 = z_s / dt.
+    //   (1-Θ) y0 + Θ y1 + Θ (Θ-1) ((1-2Θ)(y1-y0) + (Θ-1) dt k1 + Θ dt k2)
+    // MuladdMacro keeps the first product of a sum and folds the later ones in as muladd(prod(1..n-1), last, acc).
     static DEGK_DEV void interp(const Keep& K, T theta, T h, const T (&uprev)[N],
                                 const T (&unew)[N], const T* p, T tprev, T (&out)[N]) {
         (void)p; (void)tprev;
-        const T th1 = (T)1 - theta;
+        const T th1 = (T)1 - theta, thm = theta - (T)1;
+        const T w0 = fma_((T)-2, theta, (T)1);
+        const T w1 = thm * h, w2 = theta * h, w3 = theta * thm;
         DEGK_UNROLL for (int c = 0; c < N; ++c) {
-            const T dy = unew[c] - uprev[c];
-            const T inner = (th1 - theta) * dy + (theta - (T)1) * (h * K.k1[c]) + theta * (h * K.k2[c]);
-            out[c] = th1 * uprev[c] + theta * unew[c] + theta * (theta - (T)1) * inner;
+            T inner = w0 * (unew[c] - uprev[c]);
+            inner = fma_(w1, K.k1next[c], inner);
+            inner = fma_(w2, K.k2[c], inner);
+            out[c] = fma_(w3, inner, fma_(theta, unew[c], th1 * uprev[c]));
         }
     }
+    // the deferred-save replay (degk_ode_kernels2.cuh) must rebuild the *adaptive* step's k1 / k2
+    static constexpr bool REPLAY_ADAPTIVE = true;
 };
 
 template <class T, class M> using Kvaerno3M = Kvaerno<T, M, false>;

@@ -57,6 +57,11 @@ DEGK_DEV void rec_copy(R* dst, const R* src) {
 }
 
 // ------------------------------------------------------------------------------------------
+// steppers whose fixed-dt and adaptive attempts keep different interpolation data (Kvaerno) say so
+template <class...> struct replay_void_ { typedef void type; };
+template <class M, class = void> struct replay_adaptive_of { static constexpr bool value = false; };
+template <class M> struct replay_adaptive_of<M, typename replay_void_<decltype(M::REPLAY_ADAPTIVE)>::type> { static constexpr bool value = M::REPLAY_ADAPTIVE; };
+
 // One warp processes up to 32 queued save records, one per lane (scalar method).
 template <class T, class Model, class MethodS>
 DEGK_DEV void process_saves(const KArgs& a, const SaveRec<T, Model::N>* q, int first, int count,
@@ -76,7 +81,7 @@ DEGK_DEV void process_saves(const KArgs& a, const SaveRec<T, Model::N>* q, int f
         const T tprev = r.tprev, h = r.h, tnew = r.tnew;
         typename MethodS::Keep K;
         MethodS::init(K, uprev, p, tprev);                  // FSAL k1 = f(uprev, p, tprev)
-        MethodS::template attempt<false>(K, uprev, p, tprev, h, unew, err);
+        MethodS::template attempt<replay_adaptive_of<MethodS>::value>(K, uprev, p, tprev, h, unew, err);
         MethodS::on_accept(K);
         int cur = r.cur;
         while (cur <= a.n_saveat && sv[cur - 1] <= tnew) {  // integrator_utils.jl:34-47

@@ -61,8 +61,8 @@ typedef enum {
     DEGK_ALG_RODAS5P = 5,      /* GPURodas5P      */
     DEGK_ALG_EM = 6,           /* GPUEM           */
     DEGK_ALG_SIEA = 7,         /* GPUSIEA         */
-    DEGK_ALG_KVAERNO3 = 8,     /* GPUKvaerno3 (ESDIRK + Newton; endpoints / every-step output only: the reference
-                                  defines no dense output for these integrators) */
+    DEGK_ALG_KVAERNO3 = 8,     /* GPUKvaerno3 (ESDIRK + Newton; saveat through the default Hermite interpolant,
+                                  nonstiff/interpolants.jl:1-21) */
     DEGK_ALG_KVAERNO5 = 9      /* GPUKvaerno5     */
 } degk_alg;
 

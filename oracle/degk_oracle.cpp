@@ -892,7 +892,6 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
     std::vector<T> tstops_T(a.n_tstops);
     for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
     if ((a.n_tstops > 0 || a.n_cb > 0 || a.n_cc > 0) && (a.alg == A_EM || a.alg == A_SIEA || a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -3;   // events: RK / Rosenbrock steppers
-    if (saveat && (a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -4;   // no dense output in the reference
     if (a.model == M_ROBER_DAE && a.alg != A_ROS23 && a.alg != A_RODAS4 && a.alg != A_RODAS5P) return -5;   // mass matrices: Rosenbrock family
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < a.n_traj; ++i) {

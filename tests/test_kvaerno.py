@@ -44,9 +44,25 @@ def test_oracle_kvaerno_regression(oracle, alg):
     r = oracle.solve("rober", alg, [1, 0, 0], k, [0, 1e5], dt=1e-4, adaptive=True, abstol=1e-10, reltol=1e-8,
                      save_everystep=False, dtype=f64)
     assert np.allclose(r["us"][0, 1], [1.78659e-2, 7.27475e-8, 9.82134e-1], rtol=1e-4)
-    # no dense output in the reference: saveat is refused
-    with pytest.raises(RuntimeError):
-        oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.01, saveat=np.array([2.0, 4.0], f32))
+    # "solve parameters", :62-118: saveat = [2, 4] and 0:0.1:10 through the default Hermite interpolant
+    # (the reference bounds against OrdinaryDiffEq's Rosenbrock23 are 2e-4 / 2e-3 fixed and 2e-3 / 3e-2 adaptive)
+    sv = np.array([2.0, 4.0], f32)
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.01, saveat=sv)
+    a = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.01, adaptive=True, abstol=1e-7, reltol=1e-7, saveat=sv)
+    exact = 10 * np.exp(-sv.astype(f64))
+    assert np.array_equal(r["ts"][0], sv) and np.linalg.norm(r["us"][0, :, 0] - exact) < 2e-4
+    assert np.array_equal(a["ts"][0], sv) and np.linalg.norm(a["us"][0, :, 0] - exact) < 2e-3
+    assert np.linalg.norm(a["us"][0, -1] - r["us"][0, -1]) < 4e-2
+    sv = np.arange(0, 101, dtype=f32) * f32(0.1)
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.01, saveat=sv)
+    a = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.01, adaptive=True, abstol=1e-7, reltol=1e-7, saveat=sv)
+    exact = 10 * np.exp(-sv.astype(f64))
+    assert r["us"].shape[1] == 101 and np.linalg.norm(r["us"][0, :, 0] - exact) < 2e-3
+    assert np.linalg.norm(a["us"][0, :, 0] - exact) < 3e-2
+    # Float64: the interpolation error of the Hermite cubic between accepted steps stays at the tolerance level
+    a = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.01, adaptive=True, abstol=1e-9, reltol=1e-9,
+                     saveat=sv.astype(f64), dtype=f64)
+    assert np.abs(a["us"][0, :, 0] - 10 * np.exp(-sv.astype(f32).astype(f64))).max() < 1e-5
 
 
 def _gpu(dg, func, alg, u0, p, tspan, *, adaptive, autodiff=True, fp_mode="strict", dtype=f32, **kw):
@@ -109,6 +125,18 @@ def test_gpu_kvaerno_bit_exact(oracle, alg):
              save_everystep=False)
     r = oracle.solve("linear15", alg, u15, None, [0, 1], dt=0.01, adaptive=True, abstol=1e-6, reltol=1e-6, save_everystep=False)
     _same(g, r, "linear15")
-    # saveat is refused like in the reference (no _ode_interpolant method for these integrators)
-    with pytest.raises(dg.DegkError, match="dense output"):
-        _gpu(dg, dg.models.decay, alg, u0, p, [0, 10], adaptive=True, saveat=np.array([2.0, 4.0], f32), **{k_: v for k_, v in gkw.items() if k_ != "save_everystep"})
+    # saveat (gpu_ode_regression.jl:62-118): default Hermite interpolant, fixed dt and adaptive (deferred-save replay)
+    for sv in (np.array([2.0, 4.0], f32), np.arange(0, 101, dtype=f32) * f32(0.1)):
+        g = _gpu(dg, dg.models.decay, alg, u0, p, [0, 10], adaptive=False, dt=f32(0.01), saveat=sv)
+        _same(g, oracle.solve("decay", alg, u0, p, [0, 10], dt=0.01, saveat=sv), f"fixed saveat {len(sv)}")
+        g = _gpu(dg, dg.models.decay, alg, u0, p, [0, 10], adaptive=True, dt=f32(0.01), abstol=f32(1e-7), reltol=f32(1e-7), saveat=sv)
+        _same(g, oracle.solve("decay", alg, u0, p, [0, 10], dt=0.01, adaptive=True, abstol=1e-7, reltol=1e-7, saveat=sv),
+              f"adaptive saveat {len(sv)}")
+        assert np.abs(g["us"][:, :, 0] - u0 * np.exp(-p * sv[None].astype(f64))).max() < 3e-2
+    rsv = np.array([1.0, 10.0, 100.0, 1e3], f32)
+    g = _gpu(dg, dg.models.rober, alg, [1, 0, 0], k, [0, 1e3], adaptive=True, dt=f32(1e-4), abstol=f32(1e-8), reltol=f32(1e-4), saveat=rsv)
+    r = oracle.solve("rober", alg, [1, 0, 0], k, [0, 1e3], dt=1e-4, adaptive=True, abstol=1e-8, reltol=1e-4, saveat=rsv)
+    _same(g, r, "rober saveat")
+    gf = _gpu(dg, dg.models.rober, alg, [1, 0, 0], k, [0, 1e3], adaptive=True, fp_mode="fast", dt=f32(1e-4), abstol=f32(1e-8),
+              reltol=f32(1e-4), saveat=rsv)
+    assert (gf["retcode"] == 1).all() and np.abs(gf["us"] - g["us"]).max() < 2e-3
