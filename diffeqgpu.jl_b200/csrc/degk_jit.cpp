@@ -240,8 +240,8 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
             src += "\n    }\n";
         }
         if (d->mass_src) {
-            if (d->alg != DEGK_ALG_ROSENBROCK23 && d->alg != DEGK_ALG_RODAS4 && d->alg != DEGK_ALG_RODAS5P) {
-                degk_set_error(ctx, "mass matrices are lowered for the Rosenbrock family only (GPURosenbrock23, GPURodas4, GPURodas5P)");
+            if (!stiff) {
+                degk_set_error(ctx, "mass matrices need an implicit solver (GPURosenbrock23, GPURodas4, GPURodas5P, GPUKvaerno3, GPUKvaerno5)");
                 return DEGK_ERR_UNSUPPORTED;
             }
             src += "    static constexpr bool HAS_MASS = true;\n"
@@ -264,8 +264,8 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
     } else {
         const char* st = d->builtin ? builtin_struct(d->builtin) : nullptr;
         if (!st) { degk_set_error(ctx, "unknown built-in model '%s'", d->builtin ? d->builtin : "(null)"); return DEGK_ERR_INVALID; }
-        if (strcmp(d->builtin, "rober_dae") == 0 && !(d->alg >= DEGK_ALG_ROSENBROCK23 && d->alg <= DEGK_ALG_RODAS5P)) {
-            degk_set_error(ctx, "mass matrices are lowered for the Rosenbrock family only (GPURosenbrock23, GPURodas4, GPURodas5P)");
+        if (strcmp(d->builtin, "rober_dae") == 0 && !stiff) {
+            degk_set_error(ctx, "mass matrices need an implicit solver (GPURosenbrock23, GPURodas4, GPURodas5P, GPUKvaerno3, GPUKvaerno5)");
             return DEGK_ERR_UNSUPPORTED;
         }
         src += "#include \"degk_models.cuh\"\n";

@@ -47,27 +47,44 @@ struct Kvaerno {
     static DEGK_DEV void accepted_sel(Keep& K, unsigned m) { if (m & 1u) accepted(K); }
     static DEGK_DEV void accepted_if(Keep& K, const bool* acc) { if (acc[0]) accepted(K); }
 
+    // W = -mass_matrix + gamma dt J (nlsolve/type.jl:139); identity: the literal -1 on the diagonal
+    template <int MN>
+    static DEGK_DEV void set_W(T (&W)[N][N], const T (&J)[N][N], const T (&Mm)[MN][MN], T gdt) {
+        if constexpr (MN == N && has_mass_of<Model>::value) {
+            DEGK_UNROLL for (int i = 0; i < N; ++i)
+                DEGK_UNROLL for (int j = 0; j < N; ++j) W[i][j] = -Mm[i][j] + gdt * J[i][j];
+        } else {
+            DEGK_UNROLL for (int i = 0; i < N; ++i)
+                DEGK_UNROLL for (int j = 0; j < N; ++j) W[i][j] = (i == j) ? (T)-1 + gdt * J[i][j] : gdt * J[i][j];
+        }
+    }
+
     // nlsolve/utils.jl:1-26.  z: in = predictor, out = solution; tmp = explicit part of the stage
     static DEGK_DEV bool nlsolve(T (&z)[N], const T (&tmp)[N], T gam, T c, T dt, T tb, const T* p) {
         const T abstol = (T)100 * (sizeof(T) == 4 ? (T)1.1920928955078125e-7f : (T)2.220446049250313e-16);
         const T ts = tb + c * dt;
         const T gdt = gam * dt;
+        // a constant mass matrix enters here only: W = -M + gamma dt J, residual dt f - M z (utils.jl:10-21, type.jl:139)
+        constexpr bool MASS = has_mass_of<Model>::value;
+        T Mm[MASS ? N : 1][MASS ? N : 1];
+        if constexpr (MASS) Model::template mass<T>(Mm);
         for (int it = 0; it < 30; ++it) {
-            T us[N], J[N][N], W[N][N], fe[N], rhs[N], dz[N];
+            T us[N], J[N][N], W[N][N], fe[N], rhs[N], dz[N], mz[N];
             DEGK_UNROLL for (int i = 0; i < N; ++i) us[i] = tmp[i] + gam * z[i];
             eval_jac<T, Model>(J, us, p, ts);
-            DEGK_UNROLL for (int i = 0; i < N; ++i)
-                DEGK_UNROLL for (int j = 0; j < N; ++j) W[i][j] = (i == j) ? (T)-1 + gdt * J[i][j] : gdt * J[i][j];
+            set_W(W, J, Mm, gdt);
             Model::template f<T>(fe, us, p, ts);
-            DEGK_UNROLL for (int i = 0; i < N; ++i) rhs[i] = dt * fe[i] - z[i];
+            if constexpr (MASS) mass_mul<T, N>(Mm, z, mz); else { DEGK_UNROLL for (int i = 0; i < N; ++i) mz[i] = z[i]; }
+            DEGK_UNROLL for (int i = 0; i < N; ++i) rhs[i] = dt * fe[i] - mz[i];
             LinSolve<T, N> F;
             if (!F.factor(W)) return false;
             F.solve(rhs, dz);
             DEGK_UNROLL for (int i = 0; i < N; ++i) z[i] = z[i] - dz[i];
             DEGK_UNROLL for (int i = 0; i < N; ++i) us[i] = tmp[i] + gam * z[i];
             Model::template f<T>(fe, us, p, ts);
+            if constexpr (MASS) mass_mul<T, N>(Mm, z, mz); else { DEGK_UNROLL for (int i = 0; i < N; ++i) mz[i] = z[i]; }
             T acc = (T)0;
-            DEGK_UNROLL for (int i = 0; i < N; ++i) { const T r = dt * fe[i] - z[i]; acc = (i == 0) ? r * r : acc + r * r; }
+            DEGK_UNROLL for (int i = 0; i < N; ++i) { const T r = dt * fe[i] - mz[i]; acc = (i == 0) ? r * r : acc + r * r; }
             if (sqrt_(acc / (T)N) < abstol) break;           // diffeqgpunorm, src/utils.jl:1
         }
         return true;
@@ -165,8 +182,10 @@ struct Kvaerno {
             T J[N][N], W[N][N];
             const T gdt = gam * h;
             eval_jac<T, Model>(J, unew, p, tb + (T)1 * h);
-            DEGK_UNROLL for (int i = 0; i < N; ++i)
-                DEGK_UNROLL for (int j = 0; j < N; ++j) W[i][j] = (i == j) ? (T)-1 + gdt * J[i][j] : gdt * J[i][j];
+            constexpr bool MASS = has_mass_of<Model>::value;
+            T Mm[MASS ? N : 1][MASS ? N : 1];
+            if constexpr (MASS) Model::template mass<T>(Mm);
+            set_W(W, J, Mm, gdt);
             LinSolve<T, N> F;
             if (!F.factor(W)) return false;
             F.solve(b, err);

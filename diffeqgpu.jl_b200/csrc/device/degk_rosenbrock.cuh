@@ -10,7 +10,8 @@
 // (cofactors + det for n<=3, partial-pivot LU for n>=4) and each stage only does the
 // substitution.  The values are identical to recomputing (same expressions), so the strict
 // build stays bit-equal to the oracle.
-// Mass matrix = identity (UniformScaling); mass-matrix/DAE problems are SURVEY §8(f) "next".
+// A constant mass matrix (Model::HAS_MASS) enters W and the stage right-hand sides; models without one
+// keep the identity forms.
 #pragma once
 #include "degk_common.cuh"
 #include "degk_pack.cuh"

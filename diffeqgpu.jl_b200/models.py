@@ -72,6 +72,13 @@ rober_dae = ODEFunction(builtin="rober_dae", force_jit=True)
 rober_dae_src = ODEFunction(rhs=ROBER_DAE_RHS, jac=ROBER_DAE_JAC, mass_matrix="    Mm[0][0] = (T)1; Mm[1][1] = (T)1;\n",
                             n_state=3, n_param=3)
 
+# 2-state index-1 DAE with M = diag(1, 0): test/gpu_kernel_de/stiff_ode/gpu_ode_modelingtoolkit_dae.jl:22-44
+# (the literals -0.04f0 and 1.0f4 of `dae_f` as parameters)
+LIN_DAE_RHS = "    du[0] = -p[0] * u[0] + p[1] * u[1];\n    du[1] = u[0] + u[1] - (T)1;\n"
+LIN_DAE_JAC = "    J[0][0] = -p[0];  J[0][1] = p[1];\n    J[1][0] = (T)1;   J[1][1] = (T)1;\n"
+lin_dae_src = ODEFunction(rhs=LIN_DAE_RHS, jac=LIN_DAE_JAC, mass_matrix="    Mm[0][0] = (T)1;\n", n_state=2, n_param=2,
+                          python=lambda u, p, t: np.array([-p[0] * u[0] + p[1] * u[1], u[0] + u[1] - 1]))
+
 # bouncing ball x'' = -g: test/gpu_kernel_de/gpu_ode_continuous_callbacks.jl:6-10
 BALL_RHS = "    du[0] = u[1];\n    du[1] = -p[0];\n"
 ball_src = ODEFunction(rhs=BALL_RHS, n_state=2, n_param=1, python=lambda u, p, t: np.array([u[1], -p[0]]))

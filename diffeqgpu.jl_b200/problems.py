@@ -36,7 +36,7 @@ class ODEFunction:
     n_param: int = 0
     python: Optional[Callable] = field(default=None, compare=False)
     force_jit: bool = False
-    mass_matrix: Optional[str] = None   # body assigning Mm[i][j] of a constant mass matrix (Rosenbrock family), None = identity
+    mass_matrix: Optional[str] = None   # body assigning Mm[i][j] of a constant mass matrix (stiff solvers), None = identity
     use_jac: bool = True      # False: ignore the analytic Jacobian (the function "has no jac"), for the AD / FD paths
 
     def __post_init__(self):

@@ -135,9 +135,9 @@ typedef struct {
     int32_t jac_mode;
     int32_t reserved;
     /* constant mass matrix M of  M u' = f(u, p, t)  (ODEFunction(f; mass_matrix = M), src/utils.jl:42-57):
-     * body assigning Mm[i][j] (zero-initialised), NULL = identity.  Rosenbrock family only (GPURosenbrock23,
-     * GPURodas4, GPURodas5P -- the steppers whose perform_step reads f.mass_matrix); u0 must be consistent
-     * (no DAE initialisation). */
+     * body assigning Mm[i][j] (zero-initialised), NULL = identity.  Implicit solvers only (GPURosenbrock23,
+     * GPURodas4, GPURodas5P: perform_step reads f.mass_matrix; GPUKvaerno3/5: nlsolve does); u0 must be
+     * consistent (no DAE initialisation). */
     const char* mass_src;
     /* Continuous callbacks (GPUContinuousCallback, callbacks.jl:38-124; same kernels as `events`).
      * cc_condition_src[c]: body RETURNING the value of condition(u, t, integrator) (a root function);

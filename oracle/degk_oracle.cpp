@@ -87,7 +87,8 @@ enum ModelId { M_LORENZ = 0, M_HENON_HEILES = 1, M_ROBER = 2, M_DECAY = 3, M_LIN
                M_GBM = 5, M_LORENZ_ADDITIVE = 6, M_SCALAR_SDE = 7, M_OSC_T = 8, M_GBM_ND = 9,
                M_QUAD_DECAY = 10,
                M_ROBER_DAE = 11,
-               M_BALL = 12 };         // bouncing ball x'' = -g: test/gpu_kernel_de/gpu_ode_continuous_callbacks.jl:6-10    // Robertson DAE + mass matrix diag(1,1,0): stiff_ode/gpu_ode_mass_matrix.jl:5-31   // du = -p u^2: test/gpu_kernel_de/finite_diff.jl:6-9, forward_diff.jl
+               M_BALL = 12,
+               M_LIN_DAE = 13 };      // 2-state index-1 DAE, M = diag(1, 0): stiff_ode/gpu_ode_modelingtoolkit_dae.jl:22-44         // bouncing ball x'' = -g: test/gpu_kernel_de/gpu_ode_continuous_callbacks.jl:6-10    // Robertson DAE + mass matrix diag(1,1,0): stiff_ode/gpu_ode_mass_matrix.jl:5-31   // du = -p u^2: test/gpu_kernel_de/finite_diff.jl:6-9, forward_diff.jl
 
 struct ModelInfo { int n, np, m; bool has_jac; bool diag_noise; };
 
@@ -106,6 +107,7 @@ inline ModelInfo model_info(int id) {
     case M_QUAD_DECAY:      return {1, 1, 0, true, true};
     case M_ROBER_DAE:       return {3, 3, 0, true, true};
     case M_BALL:            return {2, 1, 0, true, true};
+    case M_LIN_DAE:         return {2, 2, 0, true, true};
     }
     return {0, 0, 0, false, true};
 }
@@ -195,15 +197,20 @@ inline void model_f(int id, T* du, const T* u, const T* p, T t) {
         du[0] = u[1];
         du[1] = -p[0];
         break;
+    case M_LIN_DAE:        // dae_f with the literals -0.04f0, 1.0f4 as parameters (sweepable)
+        du[0] = -p[0] * u[0] + p[1] * u[1];
+        du[1] = u[0] + u[1] - (T)1;
+        break;
     }
 }
 
 // constant mass matrix of the model; returns false for the identity (UniformScaling)
 template <class T>
 inline bool model_mass(int id, T (*Mm)[MAXN]) {
-    if (id != M_ROBER_DAE) return false;
+    if (id != M_ROBER_DAE && id != M_LIN_DAE) return false;
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Mm[i][j] = (T)0;
-    Mm[0][0] = (T)1; Mm[1][1] = (T)1;
+    Mm[0][0] = (T)1;
+    if (id == M_ROBER_DAE) Mm[1][1] = (T)1;
     return true;
 }
 
@@ -237,6 +244,10 @@ inline void model_jac(int id, T (*J)[MAXN], const T* u, const T* p, T t) {
         break;
     case M_BALL:
         J[0][1] = (T)1;
+        break;
+    case M_LIN_DAE:        // dae_jac, :32-37
+        J[0][0] = -p[0];  J[0][1] = p[1];
+        J[1][0] = (T)1;   J[1][1] = (T)1;
         break;
     case M_ROBER_DAE:      // the test passes no jac (ForwardDiff); rows 1-2 as rober_jac (:14-22), row 3 of the constraint
         J[0][0] = p[0] * (T)-1;  J[0][1] = u[2] * p[2];                                J[0][2] = p[2] * u[1];
@@ -892,7 +903,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
     std::vector<T> tstops_T(a.n_tstops);
     for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
     if ((a.n_tstops > 0 || a.n_cb > 0 || a.n_cc > 0) && (a.alg == A_EM || a.alg == A_SIEA || a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -3;   // events: RK / Rosenbrock steppers
-    if (a.model == M_ROBER_DAE && a.alg != A_ROS23 && a.alg != A_RODAS4 && a.alg != A_RODAS5P) return -5;   // mass matrices: Rosenbrock family
+    if ((a.model == M_ROBER_DAE || a.model == M_LIN_DAE) && (a.alg < A_ROS23 || a.alg == A_EM || a.alg == A_SIEA)) return -5;   // mass matrices: implicit steppers
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < a.n_traj; ++i) {
         const T* ui = u0 + i * a.u0_stride;

@@ -14,7 +14,7 @@ _LIB_PATH = _HERE / "_build" / "libdegk_oracle.so"
 _SRCS = ("degk_oracle.cpp", "oracle_stiff.inc", "oracle_kvaerno.inc", "oracle_sde.inc", "oracle_tables.inc")
 
 MODELS = {"lorenz": 0, "henon_heiles": 1, "rober": 2, "decay": 3, "linear15": 4, "gbm": 5,
-          "lorenz_additive": 6, "scalar_sde": 7, "osc_t": 8, "gbm_nd": 9, "quad_decay": 10, "rober_dae": 11, "ball": 12}
+          "lorenz_additive": 6, "scalar_sde": 7, "osc_t": 8, "gbm_nd": 9, "quad_decay": 10, "rober_dae": 11, "ball": 12, "lin_dae": 13}
 ALGS = {"tsit5": 0, "vern7": 1, "vern9": 2, "rosenbrock23": 3, "rodas4": 4, "rodas5p": 5,
         "em": 6, "siea": 7, "kvaerno3": 8, "kvaerno5": 9}
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",

@@ -42,10 +42,27 @@ def test_oracle_robertson_dae(oracle):
     a = oracle.solve("rober_dae", "rosenbrock23", [1, 0, 0], k, [0, 1e3], dt=0.1, adaptive=True, abstol=1e-5, reltol=1e-5, save_everystep=False)
     b = oracle.solve("rober_dae", "rosenbrock23", [1, 0, 0], k, [0, 1e3], dt=0.1, adaptive=True, abstol=1e-5, reltol=1e-5, save_everystep=False, jac_mode=2)
     assert np.array_equal(a["us"], b["us"])
-    # other solver families: not lowered
-    for alg in ("tsit5", "kvaerno3"):
+    # explicit solvers: no mass matrix
+    for alg in ("tsit5", "vern9"):
         with pytest.raises(RuntimeError):
             oracle.solve("rober_dae", alg, [1, 0, 0], k, [0, 1.0], dt=0.1, adaptive=True, save_everystep=False)
+
+
+STIFF = ["rosenbrock23", "rodas4", "rodas5p", "kvaerno3", "kvaerno5"]
+
+
+@pytest.mark.parametrize("alg", STIFF)
+def test_oracle_direct_mass_matrix_dae(oracle, alg):
+    """stiff_ode/gpu_ode_modelingtoolkit_dae.jl:22-112 ("Direct mass matrix DAE"): M = diag(1, 0), fixed dt = 0.001 on
+    (0, 0.1) with all five stiff solvers; `!any(isnan, u_end)` and `|u1 + u2 - 1| < 0.01`.  The Kvaerno steppers
+    see the mass matrix inside their Newton iteration only (nlsolve/utils.jl:10-21)."""
+    r = oracle.solve("lin_dae", alg, [1.0, 0.0], [0.04, 1e4], [0, 0.1], dt=0.001, length=102)
+    ts, us = r["ts"][0], r["us"][0]
+    last = np.nonzero(ts != 0)[0][-1]
+    assert r["retcode"][0] == 1 and ts[last] == f32(0.1) and not np.isnan(us[:last + 1]).any()
+    assert abs(us[last].sum() - 1) < 0.01
+    # beyond the reference's bound: the differential state relaxes to k2 / (k1 + k2) within a few steps
+    assert abs(us[last, 0] - 1e4 / (1e4 + 0.04)) < 1e-6 and abs(us[last, 1] - 0.04 / (1e4 + 0.04)) < 1e-7
 
 
 @pytest.mark.parametrize("alg", ["rodas4", "rodas5p"])
@@ -83,12 +100,16 @@ def test_mass_matrix_lowering_compiles():
                                n_state=3, n_param=3, dtype=_lib.F32, alg=alg, fp_mode=fp)
             st, nb, log = _lib.jit_compile_check(d)
             assert st == 0 and nb > 0, log
-    for alg in (0, 8):                                            # GPUTsit5, GPUKvaerno3: refused, user bodies and built-in
+    d = _lib.make_desc(rhs_src=dg.models.LIN_DAE_RHS, jac_src=dg.models.LIN_DAE_JAC, mass_src="Mm[0][0] = (T)1;", n_state=2, n_param=2,
+                       dtype=_lib.F32, alg=9)                     # GPUKvaerno5: M inside the Newton iteration
+    st, nb, log = _lib.jit_compile_check(d)
+    assert st == 0 and nb > 0, log
+    for alg in (0, 2):                                            # GPUTsit5, GPUVern9: refused, user bodies and built-in
         st, _, log = _lib.jit_compile_check(_lib.make_desc(rhs_src=dg.models.ROBER_DAE_RHS, mass_src="Mm[0][0] = (T)1;", n_state=3,
                                                            n_param=3, dtype=_lib.F32, alg=alg))
-        assert st == _lib.ERR_UNSUPPORTED and "Rosenbrock family only" in log
+        assert st == _lib.ERR_UNSUPPORTED and "implicit solver" in log
         st, _, log = _lib.jit_compile_check(_lib.make_desc(builtin="rober_dae", dtype=_lib.F32, alg=alg, force_jit=True))
-        assert st == _lib.ERR_UNSUPPORTED and "Rosenbrock family only" in log
+        assert st == _lib.ERR_UNSUPPORTED and "implicit solver" in log
 
 
 @pytest.mark.gpu
@@ -168,3 +189,27 @@ def test_gpu_robertson_dae_rodas_bit_exact(oracle, alg):
     both = ok & (gf["retcode"] == 1)
     assert both.mean() > 0.9 and np.abs(gf["us"][both] - g["us"][both]).max() < 2e-3
     assert np.abs(gf["us"][both].sum(axis=2) - 1).max() < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", STIFF)
+def test_gpu_direct_mass_matrix_dae_bit_exact(oracle, alg):
+    """the reference's "Direct mass matrix DAE" cases (fixed dt, five stiff solvers) on a parameter sweep"""
+    import torch
+    import diffeqgpu_b200 as dg
+    n = 100
+    rng = np.random.default_rng(8)
+    p = (np.array([0.04, 1e4]) * (0.5 + rng.random((n, 2)))).astype(f32)
+    Alg = dict(rosenbrock23=dg.GPURosenbrock23, rodas4=dg.GPURodas4, rodas5p=dg.GPURodas5P, kvaerno3=dg.GPUKvaerno3,
+               kvaerno5=dg.GPUKvaerno5)[alg]
+    prob = dg.ODEProblem(dg.models.lin_dae_src, np.array([1, 0], f32), (0.0, 0.1), p[0])
+    probs = dg.ProblemBatch.from_arrays(prob, p=p, device="cuda:0")
+    for kw in (dict(), dict(save_everystep=False), dict(saveat=np.array([0.0, 0.05, 0.1], f32))):
+        ts, us, st = dg.vectorized_solve(probs, prob, Alg(), dt=f32(0.001), stats=True, **kw)
+        torch.cuda.synchronize()
+        g_ts, g_us = ts.cpu().numpy(), us.cpu().numpy()
+        okw = dict(kw) if kw else dict(length=g_us.shape[1])
+        r = oracle.solve("lin_dae", alg, [1.0, 0.0], p, [0, 0.1], dt=0.001, **okw)
+        assert np.array_equal(g_ts, r["ts"]) and np.array_equal(g_us, r["us"], equal_nan=True), sorted(kw)
+        assert (st["retcode"].cpu().numpy() == 1).all()
+    assert np.abs(g_us[:, -1].sum(axis=1) - 1).max() < 0.01 and not np.isnan(g_us).any()
