@@ -191,8 +191,8 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
     src += "#include \"degk_common.cuh\"\n#include \"degk_pack.cuh\"\n";
     src += std::string("#include \"") + method_header(d->alg) + "\"\n";
     const bool events = d->events != 0 || d->n_callbacks > 0 || d->n_ccallbacks > 0;
-    if (events && (is_sde || kvaerno)) {
-        degk_set_error(ctx, "tstops / callbacks are available for the explicit RK and Rosenbrock ODE solvers only");
+    if (events && is_sde) {
+        degk_set_error(ctx, "tstops / callbacks are available for the ODE solvers only");
         return DEGK_ERR_UNSUPPORTED;
     }
     if (d->n_callbacks < 0 || d->n_callbacks > 16 || (d->n_callbacks > 0 && (!d->cb_condition_src || !d->cb_affect_src))) {

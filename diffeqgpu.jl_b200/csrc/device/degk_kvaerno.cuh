@@ -32,7 +32,9 @@ struct Kvaerno {
     static constexpr bool ALWAYS_SOLVED = false;
     static constexpr int NS = K5 ? 7 : 4;
     static constexpr int NF_ATTEMPT = NS;
-    struct Keep { T k1[N]; T k1next[N]; T k2[N]; };
+    // dt_nl / tb_nl: step and time base the fixed-dt stepper hands to build_nlsolver when a tstop shortened the
+    // step -- the nominal integ.dt and the tstop itself (gpu_kvaerno3_perform_step.jl:16-24, 36-41); 0 = unset
+    struct Keep { T k1[N]; T k1next[N]; T k2[N]; T dt_nl; T tb_nl; };
 
     static DEGK_DEV T dtmin() { return (T)1.0e-14f; }     // convert(T, 1.0f-14)
     static DEGK_DEV T land()  { return (T)1.0e-14f; }
@@ -40,6 +42,7 @@ struct Kvaerno {
     static DEGK_DEV void init(Keep& K, const T (&u0)[N], const T* p, T t0) {
         Model::template f<T>(K.k1, u0, p, t0);             // u_modified = true at the first step
         DEGK_UNROLL for (int c = 0; c < N; ++c) { K.k1next[c] = K.k1[c]; K.k2[c] = (T)0; }
+        K.dt_nl = (T)0; K.tb_nl = (T)0;
     }
     static DEGK_DEV void accepted(Keep& K) { DEGK_UNROLL for (int c = 0; c < N; ++c) K.k1[c] = K.k1next[c]; }
     static DEGK_DEV void on_accept(Keep&) {}
@@ -93,7 +96,10 @@ struct Kvaerno {
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
                                  T (&unew)[N], T (&err)[N]) {
-        const T tb = WANT_ERR ? t : t + h;                   // nlsolver.t (see the header comment)
+        const bool nominal = !WANT_ERR && K.dt_nl > (T)0;
+        const T tb = WANT_ERR ? t : (nominal ? K.tb_nl : t + h);     // nlsolver.t (see the header comment)
+        const T hnl = nominal ? K.dt_nl : h;                         // nlsolver.dt
+        if (!WANT_ERR) K.dt_nl = (T)0;
         T k1[N];
         if (WANT_ERR) Model::template f<T>(k1, uprev, p, t);  // `k1 = f(uprev, p, t)` inside the retry loop
         else { DEGK_UNROLL for (int c = 0; c < N; ++c) k1[c] = K.k1[c]; }
@@ -112,17 +118,17 @@ struct Kvaerno {
             const T al31 = ((T)1 + ((T)-4 * th + (T)3 * th2)) + w * gam;
             const T al32 = ((T)-2 * th + (T)3 * th2) + w * gam;
             DEGK_UNROLL for (int c = 0; c < N; ++c) { z[1][c] = z[0][c]; tmp[c] = uprev[c] + gam * z[0][c]; }
-            if (!nlsolve(z[1], tmp, gam, gam, h, tb, p)) return false;
+            if (!nlsolve(z[1], tmp, gam, gam, hnl, tb, p)) return false;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {
                 z[2][c] = al31 * z[0][c] + al32 * z[1][c];
                 tmp[c] = (uprev[c] + a31 * z[0][c]) + a32 * z[1][c];
             }
-            if (!nlsolve(z[2], tmp, gam, c3, h, tb, p)) return false;
+            if (!nlsolve(z[2], tmp, gam, c3, hnl, tb, p)) return false;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {
                 z[3][c] = (a31 * z[0][c] + a32 * z[1][c]) + gam * z[2][c];      // yhat as prediction
                 tmp[c] = ((uprev[c] + a41 * z[0][c]) + a42 * z[1][c]) + a43 * z[2][c];
             }
-            if (!nlsolve(z[3], tmp, gam, (T)1, h, tb, p)) return false;
+            if (!nlsolve(z[3], tmp, gam, (T)1, hnl, tb, p)) return false;
         } else {
             gam = (T)0.26;
             const T a31 = (T)0.13, a32 = (T)0.84033320996790809;
@@ -136,32 +142,32 @@ struct Kvaerno {
             const T al61 = (T)-0.17281112873898072, al62 = (T)0.6235784481025847, al63 = (T)0.5492326806363959;
             const T c3 = (T)1.230333209967908, c4 = (T)0.895765984350076, c5 = (T)0.436393609858648, c6 = (T)1;
             DEGK_UNROLL for (int c = 0; c < N; ++c) { z[1][c] = z[0][c]; tmp[c] = uprev[c] + gam * z[0][c]; }
-            if (!nlsolve(z[1], tmp, gam, gam, h, tb, p)) return false;
+            if (!nlsolve(z[1], tmp, gam, gam, hnl, tb, p)) return false;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {
                 z[2][c] = al31 * z[0][c] + al32 * z[1][c];
                 tmp[c] = (uprev[c] + a31 * z[0][c]) + a32 * z[1][c];
             }
-            if (!nlsolve(z[2], tmp, gam, c3, h, tb, p)) return false;
+            if (!nlsolve(z[2], tmp, gam, c3, hnl, tb, p)) return false;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {
                 z[3][c] = (al41 * z[0][c] + al42 * z[1][c]) + al43 * z[2][c];
                 tmp[c] = ((uprev[c] + a41 * z[0][c]) + a42 * z[1][c]) + a43 * z[2][c];
             }
-            if (!nlsolve(z[3], tmp, gam, c4, h, tb, p)) return false;
+            if (!nlsolve(z[3], tmp, gam, c4, hnl, tb, p)) return false;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {
                 z[4][c] = (al51 * z[0][c] + al52 * z[1][c]) + al53 * z[2][c];
                 tmp[c] = (((uprev[c] + a51 * z[0][c]) + a52 * z[1][c]) + a53 * z[2][c]) + a54 * z[3][c];
             }
-            if (!nlsolve(z[4], tmp, gam, c5, h, tb, p)) return false;
+            if (!nlsolve(z[4], tmp, gam, c5, hnl, tb, p)) return false;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {
                 z[5][c] = (al61 * z[0][c] + al62 * z[1][c]) + al63 * z[2][c];
                 tmp[c] = (((uprev[c] + a61 * z[0][c]) + a63 * z[2][c]) + a64 * z[3][c]) + a65 * z[4][c];
             }
-            if (!nlsolve(z[5], tmp, gam, c6, h, tb, p)) return false;
+            if (!nlsolve(z[5], tmp, gam, c6, hnl, tb, p)) return false;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {
                 z[6][c] = (((a61 * z[0][c] + a63 * z[2][c]) + a64 * z[3][c]) + a65 * z[4][c]) + gam * z[5][c];
                 tmp[c] = ((((uprev[c] + a71 * z[0][c]) + a73 * z[2][c]) + a74 * z[3][c]) + a75 * z[4][c]) + a76 * z[5][c];
             }
-            if (!nlsolve(z[6], tmp, gam, (T)1, h, tb, p)) return false;
+            if (!nlsolve(z[6], tmp, gam, (T)1, hnl, tb, p)) return false;
         }
         DEGK_UNROLL for (int c = 0; c < N; ++c) {
             unew[c] = tmp[c] + gam * z[NS - 1][c];

@@ -98,6 +98,13 @@ DEGK_DEV T itp_root(F&& fz, T left, T right, int rootfind) {
 
 // handle_callbacks!, continuous part.  hdt = integ.dt (the step the dense output belongs to); dtnew is
 // the adaptive integrator's next step (nullptr for fixed dt).  Returns saved_in_cb.
+// fixed-dt steppers that build their nonlinear solver from integ.dt / integ.t (not the tstop-shortened local dt)
+// keep both in their Keep; everyone else ignores the call
+template <class K, class T>
+DEGK_DEV auto set_nominal_step(K& k, T dt, T tnew, int) -> decltype((void)(k.dt_nl = dt)) { k.dt_nl = dt; k.tb_nl = tnew; }
+template <class K, class T>
+DEGK_DEV void set_nominal_step(K&, T, T, long) {}
+
 template <class T, class Model, class Method, class CB, class SaveF>
 DEGK_DEV bool handle_continuous(const typename Method::Keep& K, T (&u)[Model::N], const T (&uprev)[Model::N], T* p,
                                 T& t, T tprev, T hdt, T tf, T* dtnew, i64& step_idx, int& event_last_time,
@@ -238,6 +245,7 @@ DEGK_DEV void ode_solve_events_body(const KArgs& a) {
             } else {
                 t = t + dt;                      // integ.t += dt precedes the stages
             }
+            set_nominal_step(K, dt, t, 0);       // steppers whose nonlinear solver keeps integ.dt / integ.t (Kvaerno)
             if (!Method::template attempt<false>(K, uprev, p, tprev, h, unew, err)) {
                 rc = RC_SINGULAR; ++nfail; break;
             }

@@ -118,7 +118,7 @@ typedef struct {
     int32_t force_jit;      /* JIT-compile even when `builtin` exists ahead of time */
     /* Events (reference: tstops + GPUDiscreteCallback, callbacks.jl:1-36, integrator_utils.jl:69-150).
      * events != 0 builds the event-capable kernel pair (always through NVRTC) that honours
-     * degk_solve_args.tstops and the callbacks below (ODE solvers: explicit RK and Rosenbrock).
+     * degk_solve_args.tstops and the callbacks below (all ODE solvers; not the SDE ones).
      * Callback c: cb_condition_src[c] is the BODY of `bool condition(u, p, t)` (must `return`),
      * cb_affect_src[c] the body of `affect!(integrator)`: it may assign u[i] and p[i] and call
      * terminate().  Callbacks run in order after every step; save_positions is (false, false)

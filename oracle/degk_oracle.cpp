@@ -902,7 +902,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
 #endif
     std::vector<T> tstops_T(a.n_tstops);
     for (int i = 0; i < a.n_tstops; ++i) tstops_T[i] = (T)a.tstops[i];
-    if ((a.n_tstops > 0 || a.n_cb > 0 || a.n_cc > 0) && (a.alg == A_EM || a.alg == A_SIEA || a.alg == A_KVAERNO3 || a.alg == A_KVAERNO5)) return -3;   // events: RK / Rosenbrock steppers
+    if ((a.n_tstops > 0 || a.n_cb > 0 || a.n_cc > 0) && (a.alg == A_EM || a.alg == A_SIEA)) return -3;   // events: ODE steppers
     if ((a.model == M_ROBER_DAE || a.model == M_LIN_DAE) && (a.alg < A_ROS23 || a.alg == A_EM || a.alg == A_SIEA)) return -5;   // mass matrices: implicit steppers
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < a.n_traj; ++i) {
@@ -947,6 +947,7 @@ int solve_T(const SolveArgs& a, const T* u0, const T* p, const T* tspan, const T
             I.qold = (T)1.0e-4; I.abstol = (T)a.abstol; I.reltol = (T)a.reltol;
             I.u_modified = true; I.naccept = I.nreject = I.nf = 0; I.retcode = RC_DEFAULT;
             I.jac_mode = a.jac_mode;
+            I.tstops = tstops_T.empty() ? nullptr : tstops_T.data(); I.n_tstops = (int)tstops_T.size(); I.tstops_idx = 0;
             drive<T>(I, a, order, t0, tf, ui, out, saveat);
             na = I.naccept; nr = I.nreject; rc = I.retcode;
         } else {

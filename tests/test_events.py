@@ -146,7 +146,7 @@ def test_callback_argument_checks():
 # GPU: the event kernels against the oracle, bit for bit in strict mode
 # ------------------------------------------------------------------------------------------
 ALGS = {"tsit5": "GPUTsit5", "vern7": "GPUVern7", "vern9": "GPUVern9", "rosenbrock23": "GPURosenbrock23",
-        "rodas4": "GPURodas4", "rodas5p": "GPURodas5P"}
+        "rodas4": "GPURodas4", "rodas5p": "GPURodas5P", "kvaerno3": "GPUKvaerno3", "kvaerno5": "GPUKvaerno5"}
 
 
 def gpu_events(dg, model, alg, u0, p, tspan, specs, *, dt, adaptive=False, abstol=1e-6, reltol=1e-3, saveat=None,
@@ -479,6 +479,62 @@ def test_gpu_stiff_bouncing_ball_bit_exact(oracle, alg):
     gs = gpu_cc(dg, alg, u0, p, [0, 10], [BOUNCE], **fkw)
     close = np.abs(gf["us"] - gs["us"]).max(axis=(1, 2)) < 5e-2
     assert close.mean() > 0.97 and (gf["retcode"] == 1).all() and (gf["us"][:, -1, 0] > -1e-2).all()
+
+
+@pytest.mark.parametrize("alg", ["kvaerno3", "kvaerno5"])
+def test_oracle_kvaerno_events(oracle, alg):
+    """tstops / callbacks of the ESDIRK steppers (gpu_kvaerno3_perform_step.jl:15-24, 86, 213-229; no reference test)"""
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.1, adaptive=True, abstol=1e-7, reltol=1e-7,
+                     save_everystep=False, tstops=[4.0], callbacks=[KICK4])
+    assert r["ts"][0, 1] == f32(10.0) and abs(r["us"][0, 1, 0] - exact_decay_with_kicks(10.0, [4.0])) < 5e-6
+    # fixed dt: the step shortened by the tstop still hands the nominal integ.dt to build_nlsolver (:36-41), so that
+    # one step integrates over 0.5 instead of 0.4 -- kept; the time grid is exact, the value carries the defect
+    r = oracle.solve("decay", alg, [10.0], [1.0], [0, 10], dt=0.5, length=22, tstops=[2.4], callbacks=[KICK])
+    assert np.allclose(r["ts"][0][:7], [0, 0.5, 1, 1.5, 2, 2.4, 2.9], atol=1e-6)
+    assert abs(r["us"][0, -1, 0] / exact_decay_with_kicks(10.0, [2.4]) - 1) < 0.05
+    # bouncing ball, fixed dt and adaptive
+    r = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 16.5], dt=0.1, length=167, continuous_callbacks=[BOUNCE])
+    last = np.nonzero(r["ts"][0] != 0)[0][-1]
+    assert r["ts"][0, last] == f32(16.5) and np.linalg.norm(r["us"][0, last] - exact_ball(16.5)) < 8e-4
+    r = oracle.solve("ball", alg, [45.0, 0.0], [10.0], [0, 16.5], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6,
+                     save_everystep=False, continuous_callbacks=[BOUNCE])
+    assert r["ts"][0, 1] == f32(16.5) and np.linalg.norm(r["us"][0, 1] - exact_ball(16.5)) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg", ["kvaerno3", "kvaerno5"])
+def test_gpu_kvaerno_events_bit_exact(oracle, alg):
+    import diffeqgpu_b200 as dg
+    n = 100
+    u0 = (10.0 + np.arange(n)[:, None] * 0.01).astype(f32)
+    p = np.ones((n, 1), f32)
+    cbs = [KICK, KICK4]
+    for kw in (dict(dt=0.5, tstops=[2.4, 4.0]), dict(dt=0.25, tstops=[2.4], saveat=np.array([0.0, 2.4, 6.0, 10.0], f32))):
+        g = gpu_events(dg, "decay", alg, u0, p, [0, 10], cbs, **kw)
+        okw = dict(kw)
+        if "saveat" not in kw:
+            okw["length"] = g["us"].shape[1]
+        r = oracle.solve("decay", alg, u0, p, [0, 10], callbacks=cbs, **okw)
+        assert_same(g, r, f"kvaerno fixed {alg} {sorted(kw)}")
+    akw = dict(dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6)
+    for kw in (dict(save_everystep=False, tstops=[4.0]), dict(saveat=np.arange(0, 11, dtype=f32), tstops=[2.4, 4.0])):
+        g = gpu_events(dg, "decay", alg, u0, p, [0, 10], cbs, **akw, **kw)
+        r = oracle.solve("decay", alg, u0, p, [0, 10], callbacks=cbs, **akw, **kw)
+        assert_same(g, r, f"kvaerno adaptive {alg} {sorted(kw)}")
+    # non-autonomous model: the nlsolver time base at a tstop-shortened step is the tstop itself
+    po = np.linspace(0.5, 2.0, 60)[:, None].astype(f32)
+    g = gpu_events(dg, "osc_t", alg, [1.0, 0.0], po, [0, 3], [], dt=0.25, tstops=[0.7, 1.9])
+    r = oracle.solve("osc_t", alg, [1.0, 0.0], po, [0, 3], dt=0.25, tstops=[0.7, 1.9], length=g["us"].shape[1])
+    # (device cos and libm cos differ in the last ulp: time grid exact, states to 1e-5)
+    assert np.array_equal(g["ts"], r["ts"]) and np.allclose(g["us"], r["us"], rtol=1e-5, atol=1e-5), f"kvaerno osc_t tstops {alg}"
+    # bouncing ball
+    rng = np.random.default_rng(9)
+    bu0 = np.stack([rng.uniform(20, 60, n), rng.uniform(-5, 5, n)], 1).astype(f32)
+    bp = rng.uniform(5, 15, (n, 1)).astype(f32)
+    for kw in (dict(dt=0.1, saveat=np.array([0.0, 4.3, 9.1], f32)), dict(dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, save_everystep=False)):
+        g = gpu_cc(dg, alg, bu0, bp, [0, 10], [BOUNCE], func=dg.models.ball_jac_src, **kw)
+        r = oracle.solve("ball", alg, bu0, bp, [0, 10], continuous_callbacks=[BOUNCE], **kw)
+        assert_same(g, r, f"kvaerno ball {alg} {sorted(kw)}")
 
 
 @pytest.mark.gpu
