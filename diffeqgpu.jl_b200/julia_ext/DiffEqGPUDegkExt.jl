@@ -25,7 +25,7 @@ struct ModelDesc
     events::Int32; n_callbacks::Int32                 # tstops / GPUDiscreteCallback lowering (degk.h)
     cb_condition_src::Ptr{Cstring}; cb_affect_src::Ptr{Cstring}
     jac_mode::Int32; reserved::Int32                  # 0 analytic/default, 1 finite differences, 2 ForwardDiff-style duals
-    mass_src::Cstring                                 # constant mass matrix body (GPURosenbrock23), C_NULL = identity
+    mass_src::Cstring                                 # constant mass matrix body (stiff solvers), C_NULL = identity
     n_ccallbacks::Int32; reserved3::Int32             # GPUContinuousCallback lowering
     cc_condition_src::Ptr{Cstring}; cc_affect_src::Ptr{Cstring}; cc_affect_neg_src::Ptr{Cstring}
     cc_rootfind::Ptr{Int32}; cc_abstol::Ptr{Float64}; cc_repeat_nudge::Ptr{Float64}; cc_dtrelax::Ptr{Float64}

@@ -113,3 +113,34 @@ def test_product_does_not_import_oracle():
         assert "oracle" not in txt.replace("the oracle", "").replace("oracle/", "").replace("oracle's", "").replace("oracle (", "").lower() \
             or "import oracle" not in txt and "from oracle" not in txt, f
         assert "import oracle" not in txt and "from oracle" not in txt and "degk_oracle" not in txt, f
+
+
+def _c_struct_fields(name):
+    """field names of `typedef struct { ... } name;` in include/degk.h, in declaration order"""
+    import re
+    h = (ROOT / "include" / "degk.h").read_text()
+    m = re.search(r"typedef struct\s*\{((?:(?!typedef struct).)*?)\}\s*%s\s*;" % name, h, re.S)
+    assert m, name
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    out = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        parts = stmt.split(",")
+        out.append(parts[0].split()[-1].strip("* "))
+        out.extend(p.strip().strip("* ") for p in parts[1:])
+    return out
+
+
+def test_bindings_mirror_the_header_field_for_field():
+    """the ctypes mirrors and the Julia `ext/` structs list the fields of include/degk.h in order"""
+    import re
+    jl = (ROOT / "diffeqgpu.jl_b200" / "julia_ext" / "DiffEqGPUDegkExt.jl").read_text()
+    for cname, jname, ctype in (("degk_model_desc", "ModelDesc", _lib.ModelDesc), ("degk_solve_args", "SolveArgs", _lib.SolveArgs)):
+        want = _c_struct_fields(cname)
+        assert [f[0] for f in ctype._fields_] == want, cname
+        body = re.search(r"struct %s\n(.*?)\nend" % jname, jl, re.S).group(1)
+        body = re.sub(r"#.*", "", body)
+        got = re.findall(r"(\w+)::", body)
+        assert got == want, (jname, got, want)
