@@ -248,3 +248,67 @@ def test_gpu_traced_sde_matches_builtin_pathwise():
         torch.cuda.synchronize()
         out.append(us.cpu().numpy())
     assert np.array_equal(out[0], out[1])
+
+
+# ---------------------------------------------------------------------------------------- fuzz (CPU)
+def _random_tree(rng, depth):
+    """a random expression over u[0..2], p[0..1], t as (source string in numpy terms)"""
+    if depth == 0 or rng.random() < 0.2:
+        k = rng.integers(0, 8)
+        return [f"u[{k}]" for k in range(3)][k] if k < 3 else ["p[0]", "p[1]", "t", f"{rng.uniform(-2, 2):.6f}", str(int(rng.integers(1, 4)))][k - 3]
+    op = rng.integers(0, 11)
+    a = _random_tree(rng, depth - 1)
+    if op <= 3:
+        b = _random_tree(rng, depth - 1)
+        return f"({a} {'+-*'[min(op, 2)]} {b})" if op < 3 else f"({a} / (1.5 + ({b}) ** 2))"
+    if op == 4:
+        return f"({a}) ** {int(rng.integers(2, 5))}"
+    if op == 5:
+        return f"np.sin({a})"
+    if op == 6:
+        return f"np.cos({a})"
+    if op == 7:
+        return f"np.exp(-({a}) ** 2)"
+    if op == 8:
+        return f"np.log(1.25 + ({a}) ** 2)"
+    if op == 9:
+        return f"np.sqrt(0.5 + ({a}) ** 2)"
+    return f"np.tanh({a})"
+
+
+def test_lowering_fuzz_against_the_host_functions(tmp_path):
+    """25 random 3-state models: the lowered rhs / symbolic jac / tgrad, compiled as C++, against the host function"""
+    import diffeqgpu_b200 as dg
+    rng = np.random.default_rng(2024)
+    n, npar, nfun = 3, 2, 25
+    pys, funcs = [], []
+    for _ in range(nfun):
+        src = "lambda u, p, t: [" + ", ".join(_random_tree(rng, 4) for _ in range(n)) + "]"
+        py = eval(src, {"np": np})
+        pys.append(py)
+        funcs.append(dg.ODEFunction.from_python(py, n, npar, jac=True))
+    code = ["#include <cmath>", "using std::sin; using std::cos; using std::exp; using std::log; using std::sqrt;"]
+    for k, f in enumerate(funcs):
+        code.append(f"""extern "C" void f{k}(double* du, double* Jo, double* dT, const double* u, const double* p, double t) {{
+    typedef double T; T J[{n}][{n}] = {{}}; for (int i = 0; i < {n}; ++i) dT[i] = 0;
+    {{ {f.rhs} }} {{ {f.jac} }} {{ {f.tgrad} }}
+    for (int i = 0; i < {n}; ++i) for (int j = 0; j < {n}; ++j) Jo[i * {n} + j] = J[i][j]; }}""")
+    src = tmp_path / "fuzz.cpp"
+    src.write_text("\n".join(code))
+    so = tmp_path / "fuzz.so"
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-ffp-contract=off", str(src), "-o", str(so)], check=True)
+    lib = ctypes.CDLL(str(so))
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)      # noqa: E731
+    for k, py in enumerate(pys):
+        for _ in range(3):
+            u = rng.uniform(-1.5, 1.5, n); p = rng.uniform(0.5, 2.0, npar); t = float(rng.uniform(0, 2))
+            du = np.zeros(n); J = np.zeros((n, n)); dT = np.zeros(n)
+            getattr(lib, f"f{k}")(ptr(du), ptr(J), ptr(dT), ptr(u), ptr(p), ctypes.c_double(t))
+            want = np.asarray(py(u, p, t), f64)
+            assert np.allclose(du, want, rtol=1e-11, atol=1e-11), (k, funcs[k].rhs)
+            h = 1e-6
+            Jfd = np.stack([(np.asarray(py(u + h * e, p, t)) - np.asarray(py(u - h * e, p, t))) / (2 * h) for e in np.eye(n)], 1)
+            Tfd = (np.asarray(py(u, p, t + h)) - np.asarray(py(u, p, t - h))) / (2 * h)
+            scale = max(1.0, np.abs(Jfd).max())
+            assert np.allclose(J, Jfd, rtol=1e-5, atol=1e-6 * scale), (k, funcs[k].jac)
+            assert np.allclose(dT, Tfd, rtol=1e-5, atol=1e-6 * max(1.0, np.abs(Tfd).max())), (k, funcs[k].tgrad)
