@@ -153,6 +153,8 @@ class _Printer(C99CodePrinter):
 
     def _print_Pow(self, e):
         b, x = e.base, e.exp
+        if x.is_Float and float(2 * x) == int(float(2 * x)):      # u ** 2.0, u ** 0.5 written with float literals
+            x = sympy.Rational(int(float(2 * x)), 2)
         bs = self.parenthesize(b, 1000, strict=True)        # atoms bare, everything else parenthesised
         if x.is_Integer and 1 <= abs(int(x)) <= 16:
             prod = " * ".join([bs] * abs(int(x)))

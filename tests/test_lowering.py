@@ -100,6 +100,10 @@ def test_lowering_keeps_two_term_expression_trees():
     assert func.jac.count("J[") == 8 and "J[0][2]" not in func.jac and func.tgrad == ""
     plain = dg.ODEFunction.from_python(lorenz_py, 3, 3)
     assert plain.jac is None and plain.tgrad is None and plain.n_state == 3 and plain.n_param == 3
+    # float-literal exponents that are integers or halves stay products / square roots (no exp-log detour, which
+    # would fail for negative bases)
+    pw = dg.ODEFunction.from_python(lambda u, p, t: [u[0] ** 2.0 + u[0] ** 0.5 + u[0] ** -1.0], 1, 0)
+    assert "u[0] * u[0]" in pw.rhs and "sqrt(u[0])" in pw.rhs and "(T)1 / (u[0])" in pw.rhs and "log" not in pw.rhs
     # shared subexpressions are hoisted once
     rob = dg.ODEFunction.from_python(rober_py, 3, 3)
     assert rob.rhs.count("const T x_") == 2 and rob.rhs.count("p[2]*u[1]*u[2]") == 1
