@@ -36,7 +36,6 @@ class LoweringError(ValueError):
 class Traced:
     """a traced scalar: Python arithmetic and numpy ufuncs build a sympy expression"""
     __slots__ = ("e",)
-    __array_priority__ = 1000
 
     def __init__(self, e):
         self.e = sympy.sympify(e)
@@ -55,16 +54,21 @@ class Traced:
             return o
         raise LoweringError(f"cannot trace a value of type {type(o).__name__}")
 
-    def __add__(self, o): return Traced(self.e + self._x(o))
-    def __radd__(self, o): return Traced(self._x(o) + self.e)
-    def __sub__(self, o): return Traced(self.e - self._x(o))
-    def __rsub__(self, o): return Traced(self._x(o) - self.e)
-    def __mul__(self, o): return Traced(self.e * self._x(o))
-    def __rmul__(self, o): return Traced(self._x(o) * self.e)
-    def __truediv__(self, o): return Traced(self.e / self._x(o))
-    def __rtruediv__(self, o): return Traced(self._x(o) / self.e)
-    def __pow__(self, o): return Traced(self.e ** self._x(o))
-    def __rpow__(self, o): return Traced(self._x(o) ** self.e)
+    def _bin(self, o, fn):
+        if isinstance(o, np.ndarray):       # let numpy broadcast element by element (object arrays of traced values)
+            return NotImplemented
+        return Traced(fn(self.e, self._x(o)))
+
+    def __add__(self, o): return self._bin(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._bin(o, lambda a, b: b + a)
+    def __sub__(self, o): return self._bin(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._bin(o, lambda a, b: b - a)
+    def __mul__(self, o): return self._bin(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._bin(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._bin(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._bin(o, lambda a, b: b / a)
+    def __pow__(self, o): return self._bin(o, lambda a, b: a ** b)
+    def __rpow__(self, o): return self._bin(o, lambda a, b: b ** a)
     def __neg__(self): return Traced(-self.e)
     def __pos__(self): return self
 

@@ -104,6 +104,9 @@ def test_lowering_keeps_two_term_expression_trees():
     # would fail for negative bases)
     pw = dg.ODEFunction.from_python(lambda u, p, t: [u[0] ** 2.0 + u[0] ** 0.5 + u[0] ** -1.0], 1, 0)
     assert "u[0] * u[0]" in pw.rhs and "sqrt(u[0])" in pw.rhs and "(T)1 / (u[0])" in pw.rhs and "log" not in pw.rhs
+    # numpy arrays of traced values: matrix-vector products, broadcasting, ufuncs
+    A = dg.ODEFunction.from_python(lambda u, p, t: np.array([[0.0, p[0]], [-1.0, 0.0]]) @ np.array(u) + np.sin(np.array(u)) * p[0], 2, 1)
+    assert "du[0] = p[0]*u[1] + p[0]*sin(u[0]);" in A.rhs.replace("p[0]*sin(u[0]) + p[0]*u[1]", "p[0]*u[1] + p[0]*sin(u[0])")
     # shared subexpressions are hoisted once
     rob = dg.ODEFunction.from_python(rober_py, 3, 3)
     assert rob.rhs.count("const T x_") == 2 and rob.rhs.count("p[2]*u[1]*u[2]") == 1
