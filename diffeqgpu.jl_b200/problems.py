@@ -120,6 +120,9 @@ class ODEProblem:
     def __post_init__(self):
         u0 = np.asarray(self.u0)
         dtype = u0.dtype if u0.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+        if callable(self.f) and not isinstance(self.f, ODEFunction):
+            # `ODEProblem{false}(f, u0, tspan, p)` with a plain host function: lowered by tracing (lowering.py)
+            object.__setattr__(self, "f", ODEFunction.from_python(self.f, u0.size, 0 if self.p is None else np.size(self.p)))
         n, npar = _dims(self.f)
         object.__setattr__(self, "u0", _as_vec(u0, dtype, n, "u0"))
         p = np.zeros(0, dtype) if self.p is None else np.asarray(self.p, dtype=dtype).reshape(-1)

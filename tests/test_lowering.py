@@ -117,6 +117,16 @@ def test_lowering_keeps_two_term_expression_trees():
         dg.ODEFunction.from_python(lorenz_py, 3, 3, mass_matrix=np.eye(2))
 
 
+def test_odeproblem_takes_a_host_function():
+    """`ODEProblem{false}(f, u0, tspan, p)` with a plain function, as in the reference's tests"""
+    import diffeqgpu_b200 as dg
+    prob = dg.ODEProblem(lorenz_py, np.array([1, 0, 0], f32), (0.0, 10.0), np.array([10, 28, 8 / 3], f32))
+    assert isinstance(prob.f, dg.ODEFunction) and prob.f.n_state == 3 and prob.f.n_param == 3 and "du[2]" in prob.f.rhs
+    assert prob.dtype == f32 and np.allclose(prob.f.python(prob.u0, prob.p, 0.0), [-10, 28, 0])
+    again = dg.remake(prob, p=np.array([1, 2, 3], f32))
+    assert again.f is prob.f                      # remake keeps the lowered function (one program for the ensemble)
+
+
 def test_lowering_refuses_what_cannot_be_traced():
     import diffeqgpu_b200 as dg
     from diffeqgpu_b200.lowering import LoweringError
