@@ -47,6 +47,30 @@ def golden_cases():
     return cases
 
 
+# cases frozen for the oracle only (events, mass matrices, the ESDIRK steppers): the GPU tests of these features
+# compare the device with a fresh oracle run on larger sweeps (test_events / test_mass_matrix / test_kvaerno)
+def golden_cases_oracle_only():
+    f32 = np.float32
+    kick = (("t_eq", 0, 2.4), ("u_add", 0, 10.0))
+    bounce = dict(condition=("u_minus", 0, 0.0), affect=("u_scale", 1, -1.0))
+    sv = np.array([2.0, 4.0])
+    cases = []
+    for alg in ("kvaerno3", "kvaerno5"):
+        cases.append((f"decay_{alg}_fixed_saveat_f32", dict(model="decay", alg=alg, u0=[10.0], p=[1.0], tspan=[0, 10], dt=0.01, saveat=sv, dtype=f32)))
+        cases.append((f"decay_{alg}_adaptive_saveat_f32", dict(model="decay", alg=alg, u0=[10.0], p=[1.0], tspan=[0, 10], dt=0.01, adaptive=True, abstol=1e-7, reltol=1e-7, saveat=sv, dtype=f32)))
+        cases.append((f"decay_{alg}_fixed_tstops_kick_f32", dict(model="decay", alg=alg, u0=[10.0], p=[1.0], tspan=[0, 10], dt=0.5, length=22, tstops=[2.4], callbacks=[kick], dtype=f32)))
+    for alg in ("rosenbrock23", "rodas4", "rodas5p", "kvaerno3", "kvaerno5"):
+        cases.append((f"lin_dae_{alg}_fixed_f32", dict(model="lin_dae", alg=alg, u0=[1.0, 0.0], p=[0.04, 1e4], tspan=[0, 0.1], dt=0.001, length=102, dtype=f32)))
+    # stiff_ode/gpu_ode_mass_matrix.jl:44-58 (GPURosenbrock23, dt = 0.1, tol 1e-5) and the Rodas steppers on a sweep
+    cases.append(("rober_dae_rosenbrock23_adaptive_f32", dict(model="rober_dae", alg="rosenbrock23", u0=U0_LORENZ, p=[0.04, 3e7, 1e4], tspan=[0, 1e5], dt=0.1, adaptive=True, abstol=1e-5, reltol=1e-5, save_everystep=False, dtype=f32)))
+    for alg in ("rodas4", "rodas5p"):
+        cases.append((f"rober_dae_{alg}_adaptive_f32", dict(model="rober_dae", alg=alg, u0=U0_LORENZ, p=rober_sweep(8), tspan=[0, 1e4], dt=1e-4, adaptive=True, abstol=1e-8, reltol=1e-4, saveat=[1.0, 1e2, 1e3, 1e4], dtype=f32)))
+    for alg in ("tsit5", "rosenbrock23", "rodas4", "kvaerno3"):
+        cases.append((f"ball_{alg}_fixed_saveat_f32", dict(model="ball", alg=alg, u0=[45.0, 0.0], p=[10.0], tspan=[0, 10], dt=0.1, saveat=[0.0, 4.3, 9.1], continuous_callbacks=[bounce], dtype=f32)))
+        cases.append((f"ball_{alg}_adaptive_f32", dict(model="ball", alg=alg, u0=[45.0, 0.0], p=[10.0], tspan=[0, 16.5], dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, save_everystep=False, continuous_callbacks=[bounce], dtype=f32)))
+    return cases
+
+
 # ------------------------------------------------------------------------------------------
 # discrete-callback specs: one description, two lowerings -- the oracle interprets the spec
 # (oracle.COND_KINDS / AFFECT_KINDS), the device gets CUDA-C bodies (include/degk.h,

@@ -14,15 +14,20 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
-from cases import golden_cases  # noqa: E402
+from cases import golden_cases, golden_cases_oracle_only  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 out = {}
-for name, kw in golden_cases():
+for name, kw in golden_cases() + golden_cases_oracle_only():
     kw = dict(kw)
     model, alg = kw.pop("model"), kw.pop("alg")
     r = oracle.solve(model, alg, kw.pop("u0"), kw.pop("p"), kw.pop("tspan"), **kw)
     for k in ("ts", "us", "naccept", "nreject", "retcode"):
         out[f"{name}/{k}"] = r[k]
     print(name, r["us"].shape, "acc", int(r["naccept"].sum()), "rej", int(r["nreject"].sum()))
-np.savez_compressed(Path(__file__).resolve().parent / "oracle_golden.npz", **out)
+path = Path(__file__).resolve().parent / "oracle_golden.npz"
+if path.exists() and "--force" not in sys.argv:      # frozen entries may only be extended, not changed
+    old = np.load(path)
+    for k in old.files:
+        assert k in out and np.array_equal(old[k], out[k], equal_nan=True), f"{k} changed (pass --force to overwrite)"
+np.savez_compressed(path, **out)

@@ -8,7 +8,7 @@ import pytest
 from scipy.integrate import solve_ivp
 
 sys.path.insert(0, str(Path(__file__).resolve().parent))
-from cases import K0_ROBER, P0_LORENZ, U0_LORENZ, golden_cases, lorenz_sweep  # noqa: E402
+from cases import K0_ROBER, P0_LORENZ, U0_LORENZ, golden_cases, golden_cases_oracle_only, lorenz_sweep  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 GOLD = np.load(Path(__file__).resolve().parent / "golden" / "oracle_golden.npz")
@@ -24,7 +24,8 @@ def truth_lorenz(tf, p=P0_LORENZ, t_eval=None):
     return s.y.T
 
 
-@pytest.mark.parametrize("name,kw", golden_cases(), ids=[c[0] for c in golden_cases()])
+@pytest.mark.parametrize("name,kw", golden_cases() + golden_cases_oracle_only(),
+                         ids=[c[0] for c in golden_cases() + golden_cases_oracle_only()])
 def test_oracle_matches_golden(name, kw):
     kw = dict(kw)
     model, alg = kw.pop("model"), kw.pop("alg")
