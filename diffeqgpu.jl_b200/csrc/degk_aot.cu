@@ -20,6 +20,7 @@
 #include "device/degk_ode_kernels.cuh"
 #include "device/degk_ode_kernels2.cuh"
 #include "device/degk_ode_kernels3.cuh"
+#include "device/degk_ode_kernels4.cuh"
 #include "device/degk_sde_kernels.cuh"
 #include "degk_internal.h"
 
@@ -27,7 +28,9 @@
 #define DEGK_A2_MINBLOCKS_F64 1   // Float64: no register cap (Vern9 needs 234); 3 blocks/SM (168 registers) spills ~500 B
 #endif
 #ifndef DEGK_A2_MINBLOCKS
-#define DEGK_A2_MINBLOCKS 4   // resident blocks per SM the Float32 adaptive kernel is compiled for (register cap 128)
+// resident blocks per SM the Float32 adaptive kernel is compiled for: 4 (128 registers) for the packed fast build,
+// 6 (80 registers) for the one-slot strict build (C2, 8.4 M trajectories: 38.0 G steps/s at 4, 41.4 at 6, 41.0 at 8)
+#define DEGK_A2_MINBLOCKS (DEGK_STRICT ? 6 : 4)
 #endif
 
 namespace degk {
@@ -49,7 +52,7 @@ template <int FPMODE, class T, class Model, template <class, class> class Method
 // was measured slower on C2 (85 vs 92 G steps/s: the spills cost more than the extra warps hide).
 __global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? DEGK_A2_MINBLOCKS : DEGK_A2_MINBLOCKS_F64)) k_ode_asolve2(const KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
-    ode_asolve_gen_body<T, Model, Method, W>(a, degk_smem);
+    ode_asolve4_body<T, Model, Method, W>(a, degk_smem);
 }
 template <int FPMODE, class T, class Model, int ALG>
 __global__ void __launch_bounds__(DEGK_BLOCK) k_sde_solve(const KArgs a) {
@@ -69,7 +72,7 @@ using namespace degk;
 
 #define DIMS(MD) MD::N, MD::NP, MD::M, MD::NOISE
 #define V2(T, MD, METHOD, W)                                                                        \
-    (const void*)&k_ode_asolve2<DEGK_STRICT, T, MD, METHOD, W>, W, asolve2_qcap<T, MD::N, W>(),     \
+    (const void*)&k_ode_asolve2<DEGK_STRICT, T, MD, METHOD, W>, W, asolve4_qcap<T, MD::N, W>(),     \
         (int)sizeof(SaveRec<T, MD::N>)
 #define NOV2 nullptr, 0, 0, 0
 // explicit RK: packed pairs for Float32 in fast mode

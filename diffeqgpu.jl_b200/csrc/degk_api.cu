@@ -64,13 +64,13 @@ void degk_set_error(degk_ctx* ctx, const char* fmt, ...) {
 
 static size_t dtype_size(int dtype) { return dtype == DEGK_F64 ? 8 : 4; }
 
-// dynamic shared memory of the second-generation adaptive kernel (degk_ode_kernels2.cuh):
-// per-warp save queues + per-warp problem pools (32 x (n + np + 2) values) + saveat copy
+// dynamic shared memory of the adaptive kernel (degk_ode_kernels4.cuh, asolve4_smem_bytes):
+// per-warp save queues + per-warp problem pools (32 x (n + np + 3) values) + saveat copy
 size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged) {
     const size_t es = dtype_size(prog->info.dtype);
     const size_t nw = DEGK_BLOCK2 / 32;
-    return nw * prog->qcap2 * prog->rec_bytes2 + nw * 32 * (size_t)(prog->info.n_state + prog->info.n_param + 2) * es +
-           ((size_t)n_saveat_staged + 2) * es;     // + two +inf sentinels (generation 3)
+    return nw * prog->qcap2 * prog->rec_bytes2 + nw * 32 * (size_t)(prog->info.n_state + prog->info.n_param + 3) * es +
+           ((size_t)n_saveat_staged + 2) * es;     // + two +inf sentinels
 }
 
 extern "C" int degk_version(void) { return DEGK_VERSION; }
@@ -222,8 +222,8 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
                 prog->info.regs_adaptive2 = fa.numRegs;
                 prog->info.local_bytes_adaptive2 = (int)fa.localSizeBytes;
                 prog->info.slots_per_thread2 = prog->w2;
-                const size_t smem = degk_smem2_bytes(prog, 1024);
-                if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(prog->fn[2], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const size_t smem = degk_smem2_bytes(prog, 1024), smem_max = degk_smem2_bytes(prog, DEGK_SAVEAT_STAGE_MAX);
+                if (smem_max > 48 * 1024) CK(ctx, cudaFuncSetAttribute(prog->fn[2], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
                 CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prog->fn[2], DEGK_BLOCK2, smem));
                 prog->info.max_blocks_per_sm2 = occ;
             }
@@ -392,9 +392,29 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     const int block = v2 ? DEGK_BLOCK2 : DEGK_BLOCK;
     const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : DEGK_BLOCK;
     size_t smem = 0;
+    void* sv_padded = nullptr;
     if (v2) {
-        const int nsv = (a->saveat && a->n_saveat <= 1024) ? a->n_saveat : 0;
-        smem = degk_smem2_bytes(prog, nsv);
+        // saveat is staged in shared memory with two +inf sentinels behind it; a grid too long for that gets a
+        // padded copy in device memory for the duration of this launch (stream-ordered allocation)
+        const bool stage = !a->saveat || a->n_saveat <= DEGK_SAVEAT_STAGE_MAX;
+        smem = degk_smem2_bytes(prog, stage && a->saveat ? a->n_saveat : 0);
+        if (!stage) {
+            const size_t es = dtype_size(prog->info.dtype);
+            const size_t nb = (size_t)a->n_saveat * es;
+            CK(ctx, cudaMallocAsync(&sv_padded, nb + 2 * es, stream));
+            CK(ctx, cudaMemcpyAsync(sv_padded, a->saveat, nb, cudaMemcpyDeviceToDevice, stream));
+            CK(ctx, cudaMemsetAsync((char*)sv_padded + nb, 0, 2 * es, stream));
+            // +inf: 0x7f800000 (float) / 0x7ff0000000000000 (double), written bytewise
+            if (es == 4) {
+                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 2, 0x80, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 3, 0x7f, 1, stream));
+                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 6, 0x80, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 7, 0x7f, 1, stream));
+            } else {
+                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 6, 0xf0, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 7, 0x7f, 1, stream));
+                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 14, 0xf0, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 15, 0x7f, 1, stream));
+            }
+            k.saveat = sv_padded;
+            k.reserved |= 1;
+        }
     }
     // fixed-dt kernel, every-step saves in the reference layout: stage R rows per lane in shared
     // memory (<= 48 KB per block, so no opt-in attribute is needed) and flush them coalesced
@@ -424,10 +444,16 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     if (blocks > 2147483647LL) { degk_set_error(ctx, "too many blocks"); return DEGK_ERR_INVALID; }
 
     const int kidx = v2 ? 2 : which;
-    if (prog->info.is_jit) return degk_jit_launch(prog, kidx, (unsigned)blocks, (unsigned)block, (unsigned)smem, &k, stream);
-    void* params[1] = {(void*)&k};
-    CK(ctx, cudaLaunchKernel(prog->fn[kidx], dim3((unsigned)blocks), dim3((unsigned)block), params, smem, stream));
-    return DEGK_OK;
+    int rc = DEGK_OK;
+    if (prog->info.is_jit) {
+        rc = degk_jit_launch(prog, kidx, (unsigned)blocks, (unsigned)block, (unsigned)smem, &k, stream);
+    } else {
+        void* params[1] = {(void*)&k};
+        cudaError_t e = cudaLaunchKernel(prog->fn[kidx], dim3((unsigned)blocks), dim3((unsigned)block), params, smem, stream);
+        if (e != cudaSuccess) { degk_set_error(ctx, "kernel launch failed: %s", cudaGetErrorString(e)); rc = DEGK_ERR_CUDA; }
+    }
+    if (sv_padded) cudaFreeAsync(sv_padded, stream);
+    return rc;
 }
 
 extern "C" int degk_solve(degk_program* prog, const degk_solve_args* a, void* stream) {

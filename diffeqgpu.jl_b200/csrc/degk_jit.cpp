@@ -201,7 +201,7 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
     }
     src += is_sde ? "#include \"degk_sde_kernels.cuh\"\n"
            : events ? "#include \"degk_ode_events.cuh\"\n"
-                    : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels2.cuh\"\n#include \"degk_ode_kernels3.cuh\"\n";
+                    : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels4.cuh\"\n";
     snprintf(buf, sizeof buf, "typedef %s REAL;\n", d->dtype == DEGK_F64 ? "double" : "float");
     src += buf;
     if (d->rhs_src) {
@@ -364,9 +364,9 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                "    degk::ode_solve_body<REAL, MODEL, METHOD>(a, degk_smem);\n}\n";   // (the first-generation adaptive kernel exists ahead of time only, for A/B runs)
         snprintf(buf, sizeof buf,
                  "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
-                 "extern \"C\" __global__ void __launch_bounds__(%d, (sizeof(REAL) == 4 ? 4 : 1)) degk_jit_adaptive2(const degk::KArgs a) {\n"
+                 "extern \"C\" __global__ void __launch_bounds__(%d, (sizeof(REAL) == 4 ? (DEGK_STRICT ? 6 : 4) : 1)) degk_jit_adaptive2(const degk::KArgs a) {\n"
                  "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
-                 "    degk::ode_asolve_gen_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
+                 "    degk::ode_asolve4_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
                  save_rec_bytes(d->dtype, d->rhs_src ? d->n_state : builtin_n_state(d->builtin)), DEGK_BLOCK2, slots);
         src += buf;
     }
@@ -491,13 +491,13 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     prog->info.max_blocks_per_sm = v;
     if (f2) {
         prog->w2 = slots;
-        prog->qcap2 = 32 + 32 * slots;
+        prog->qcap2 = (d->fp_mode != DEGK_FP_STRICT && slots == 2 && d->dtype != DEGK_F64) ? 128 : 32 + 32 * slots;   // asolve4_qcap
         prog->rec_bytes2 = save_rec_bytes(d->dtype, prog->info.n_state);
         DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, f2)); prog->info.regs_adaptive2 = v;
         DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f2)); prog->info.local_bytes_adaptive2 = v;
         prog->info.slots_per_thread2 = slots;
-        const size_t smem = degk_smem2_bytes(prog, 1024);
-        if (smem > 48 * 1024) DRV(ctx, g_drv.FuncSetAttribute(f2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+        const size_t smem = degk_smem2_bytes(prog, 1024), smem_max = degk_smem2_bytes(prog, DEGK_SAVEAT_STAGE_MAX);
+        if (smem_max > 48 * 1024) DRV(ctx, g_drv.FuncSetAttribute(f2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_max));
         DRV(ctx, g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&v, f2, DEGK_BLOCK2, smem));
         prog->info.max_blocks_per_sm2 = v;
     }
