@@ -24,15 +24,6 @@
 #include "device/degk_sde_kernels.cuh"
 #include "degk_internal.h"
 
-#ifndef DEGK_A2_MINBLOCKS_F64
-#define DEGK_A2_MINBLOCKS_F64 1   // Float64: no register cap (Vern9 needs 234); 3 blocks/SM (168 registers) spills ~500 B
-#endif
-#ifndef DEGK_A2_MINBLOCKS
-// resident blocks per SM the Float32 adaptive kernel is compiled for: 4 (128 registers) for the packed fast build,
-// 6 (80 registers) for the one-slot strict build (C2, 8.4 M trajectories: 38.0 G steps/s at 4, 41.4 at 6, 41.0 at 8)
-#define DEGK_A2_MINBLOCKS (DEGK_STRICT ? 6 : 4)
-#endif
-
 namespace degk {
 
 template <class T, class M> using Rodas4M = Rodas<T, M, false>;
@@ -48,9 +39,8 @@ __global__ void __launch_bounds__(DEGK_BLOCK) k_ode_asolve(const KArgs a) {
     ode_asolve_body<T, Model, Method<T, Model>>(a);
 }
 template <int FPMODE, class T, class Model, template <class, class> class Method, int W>
-// Float32: cap at 128 registers (4 blocks of 128 threads per SM).  Forcing 5 blocks (96 registers)
-// was measured slower on C2 (85 vs 92 G steps/s: the spills cost more than the extra warps hide).
-__global__ void __launch_bounds__(DEGK_BLOCK2, (sizeof(T) == 4 ? DEGK_A2_MINBLOCKS : DEGK_A2_MINBLOCKS_F64)) k_ode_asolve2(const KArgs a) {
+// register budget: see asolve4_minblocks (Float64: no cap -- Vern9 needs 234 registers, 3 blocks/SM spill ~500 B)
+__global__ void __launch_bounds__(DEGK_BLOCK2, (asolve4_minblocks<T, Method<T, Model>>())) k_ode_asolve2(const KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
     ode_asolve4_body<T, Model, Method, W>(a, degk_smem);
 }

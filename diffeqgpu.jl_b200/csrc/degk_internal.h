@@ -2,7 +2,9 @@
 #pragma once
 
 #define DEGK_BLOCK 256    // threads per block of the first-generation kernels (__launch_bounds__)
+#ifndef DEGK_BLOCK2
 #define DEGK_BLOCK2 128   // threads per block of the adaptive kernel (degk_ode_kernels4.cuh)
+#endif
 #define DEGK_SAVEAT_STAGE_MAX 4096   // saveat grids up to this length are staged in shared memory by the adaptive kernel
 
 struct degk_aot_entry {

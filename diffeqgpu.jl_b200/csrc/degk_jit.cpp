@@ -364,7 +364,7 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                "    degk::ode_solve_body<REAL, MODEL, METHOD>(a, degk_smem);\n}\n";   // (the first-generation adaptive kernel exists ahead of time only, for A/B runs)
         snprintf(buf, sizeof buf,
                  "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
-                 "extern \"C\" __global__ void __launch_bounds__(%d, (sizeof(REAL) == 4 ? (DEGK_STRICT ? 6 : 4) : 1)) degk_jit_adaptive2(const degk::KArgs a) {\n"
+                 "extern \"C\" __global__ void __launch_bounds__(%d, (degk::asolve4_minblocks<REAL, METHOD>())) degk_jit_adaptive2(const degk::KArgs a) {\n"
                  "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
                  "    degk::ode_asolve4_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
                  save_rec_bytes(d->dtype, d->rhs_src ? d->n_state : builtin_n_state(d->builtin)), DEGK_BLOCK2, slots);

@@ -162,6 +162,9 @@ struct Ctl {
     static DEGK_DEV T qoldinit() { return (T)1.0e-4; }
 };
 
+// stage hook of the generated explicit RK steppers (see gen_erk_*.cuh::attempt): nothing by default
+struct NoHook { template <int J, int NH> DEGK_DEV void at() {} };
+
 DEGK_DEV u32 lane_id() { u32 r; asm volatile("mov.u32 %0, %%laneid;" : "=r"(r)); return r; }
 
 template <class T> DEGK_DEV bool finite_(T x) { return (x - x) == (T)0; }

@@ -86,9 +86,21 @@ __host__ __device__ constexpr size_t asolve4_smem_bytes(int nwarps, int nsv) {
            ((size_t)nsv + 2) * sizeof(T);
 }
 
-// does the stepper offer the h-scaled attempt / dense output (generated explicit RK, FSAL, no extra stages)?
 template <class M, class = void> struct has_hk_of { static constexpr bool value = false; };
 template <class M> struct has_hk_of<M, typename replay_void_<decltype(M::HAS_HK)>::type> { static constexpr bool value = M::HAS_HK; };
+
+// resident blocks (of DEGK_BLOCK2 = 128 threads) per SM the kernel is compiled for.  Measured on C2 (Lorenz,
+// GPUTsit5, 8.4 M trajectories; tools/c2_probe.cu): packed fast build 3: 121, 4: 128, 5 (96 registers, no spills):
+// 133, 6 (80 registers, 100 B spilled): 128 G steps/s; one-slot strict build 4: 38.0, 6: 41.4, 8: 41.0.
+// Steppers with more live stage vectors (Vern7/9, the Rosenbrock family) keep the 128-register budget.
+template <class T, class MS> __host__ __device__ constexpr int asolve4_minblocks() {
+    if (sizeof(T) != 4) return 1;
+    if (!MS::ALWAYS_SOLVED) return 4;
+    if (has_hk_of<MS>::value) return DEGK_STRICT ? 6 : 5;        // FSAL, <= 7 stages
+    return 4;
+}
+
+// does the stepper offer the h-scaled attempt / dense output (generated explicit RK, FSAL, no extra stages)?
 template <class M> __host__ __device__ constexpr bool use_hk() { return !DEGK_STRICT && DEGK4_HK && has_hk_of<M>::value; }
 
 template <bool HK, class M, class V, class KeepT, int N>

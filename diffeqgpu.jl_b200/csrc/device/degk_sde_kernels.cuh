@@ -6,8 +6,10 @@
 // RNG.  The reference seeds a backend-dependent device RNG per thread (`Random.seed!(prob.seed)`,
 // gpu_em_perform_step.jl:8; degenerate on its CPU backend).  Here the stream is
 // counter based and therefore independent of launch geometry and of how an ensemble is sharded
-// over GPUs: normals for (global trajectory i, step j) = BoxMuller(Philox4x32-10(key = seed ^ i,
-// counter = (j, block, 0, 0))).  The u32 stream is bit-identical to the oracle's.
+// over GPUs: normals for (global trajectory i, step j) = BoxMuller(Philox4x32-10(key = seed,
+// counter = (j, block, i_lo, i_hi))).  Seed and trajectory index occupy different Philox words, so two seeds
+// never share a stream (with key = seed ^ i, seeds s and s ^ d would only permute the paths of an ensemble).
+// The u32 stream is bit-identical to the oracle's.
 #pragma once
 #include "degk_common.cuh"
 
@@ -55,10 +57,10 @@ DEGK_DEV void box_muller(u32 a, u32 b, double& z0, double& z1) {
 }
 
 template <class T, int MM>
-DEGK_DEV void normals_for_step(u32 k0, u32 k1, u32 step, T (&z)[MM]) {
+DEGK_DEV void normals_for_step(u32 k0, u32 k1, u32 g0, u32 g1, u32 step, T (&z)[MM]) {
     DEGK_UNROLL for (int b = 0; 4 * b < MM; ++b) {
         u32 r[4];
-        philox4x32_10(step, (u32)b, 0u, 0u, k0, k1, r);
+        philox4x32_10(step, (u32)b, g0, g1, k0, k1, r);
         T zz[4];
         box_muller(r[0], r[1], zz[0], zz[1]);
         if (4 * b + 2 < MM) box_muller(r[2], r[3], zz[2], zz[3]);
@@ -104,8 +106,8 @@ DEGK_DEV void sde_solve_body(const KArgs& a) {
     const bool has_saveat = saveat != nullptr;
     const bool red = a.reduce != nullptr;
     const u64 gid = (u64)(a.traj_offset + tl);
-    const u32 k0 = (u32)a.seed ^ (u32)gid;
-    const u32 k1 = (u32)(a.seed >> 32) ^ (u32)(gid >> 32) ^ 0x5DEECE66u;
+    const u32 k0 = (u32)a.seed, k1 = (u32)(a.seed >> 32);
+    const u32 g0 = (u32)gid, g1 = (u32)(gid >> 32);
     int cur = 0;
     i64 ts_written = 0;
     if (has_saveat) {                       // gpu_em_perform_step.jl:27-37
@@ -126,7 +128,7 @@ DEGK_DEV void sde_solve_body(const KArgs& a) {
     for (i64 j = 2; j <= nst; ++j) {
         DEGK_UNROLL for (int c = 0; c < N; ++c) uprev[c] = u[c];
         T z[MM];
-        normals_for_step<T, MM>(k0, k1, (u32)(j - 2), z);
+        normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 2), z);
         if constexpr (ALG == ALG_EM) {
             T f[N];
             Model::template f<T>(f, uprev, p, t);

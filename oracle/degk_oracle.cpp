@@ -324,11 +324,12 @@ inline void box_muller(uint32_t a, uint32_t b, T& z0, T& z1) {
 // normals for (traj, step): draws m normals; block b covers normals 4b..4b+3
 template <class T>
 inline void normals_for_step(uint64_t seed, uint64_t traj, uint32_t step, int m, T* z) {
-    uint32_t k0 = (uint32_t)seed ^ (uint32_t)traj;
-    uint32_t k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(traj >> 32) ^ 0x5DEECE66u;
+    // seed and trajectory index live in different Philox words (key = seed, counter = (step, block, traj)):
+    // two seeds never share a stream, whatever the trajectory indices are
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int b = 0; 4 * b < m; ++b) {
         uint32_t r[4];
-        philox4x32_10(step, (uint32_t)b, 0u, 0u, k0, k1, r);
+        philox4x32_10(step, (uint32_t)b, (uint32_t)traj, (uint32_t)(traj >> 32), k0, k1, r);
         T zz[4];
         box_muller<T>(r[0], r[1], zz[0], zz[1]);
         box_muller<T>(r[2], r[3], zz[2], zz[3]);

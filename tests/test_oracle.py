@@ -170,3 +170,18 @@ def test_philox_known_answer():
     assert [hex(x) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
     oracle.lib().degk_oracle_philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, out)
     assert [hex(x) for x in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+def test_sde_seeds_are_independent_streams():
+    """with key = seed ^ trajectory the ensembles of seeds s and s ^ d were permutations of each other.
+    Seed and trajectory index now sit in different Philox words."""
+    n = 64
+    u0 = np.full((n, 1), 0.5, np.float32)
+    kw = dict(dt=1 / 32, save_everystep=False)
+    a = oracle.solve("scalar_sde", "em", u0, [1.0, 0.5], [0, 1], seed=0, **kw)["us"][:, 1, 0]
+    b = oracle.solve("scalar_sde", "em", u0, [1.0, 0.5], [0, 1], seed=1, **kw)["us"][:, 1, 0]
+    a2 = oracle.solve("scalar_sde", "em", u0, [1.0, 0.5], [0, 1], seed=0, **kw)["us"][:, 1, 0]
+    assert np.array_equal(a, a2)
+    assert len(np.intersect1d(a, b)) == 0
+    # trajectory i of seed 0 is not trajectory i ^ 1 of seed 1 any more
+    assert not np.array_equal(a[np.arange(n) ^ 1], b)

@@ -23,6 +23,9 @@
 #if GEN >= 4
 #include "device/degk_ode_kernels4.cuh"
 #endif
+#if GEN >= 5
+#include "../../tools/experiments/degk_ode_kernels5.cuh"   // two-stream variant (measured slower; kept as an experiment)
+#endif
 #include "degk_internal.h"
 
 #ifndef GEN
@@ -39,7 +42,9 @@ using namespace degk;
 template <class T, class Model, template <class, class> class Method, int W>
 __global__ void __launch_bounds__(DEGK_BLOCK2, MINBLOCKS) k_probe(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
-#if GEN >= 4
+#if GEN >= 5
+    ode_asolve5_body<T, Model, Method, W>(a, degk_smem);
+#elif GEN >= 4
     ode_asolve4_body<T, Model, Method, W>(a, degk_smem);
 #elif GEN == 3 && !DEGK_STRICT
     ode_asolve3_body<T, Model, Method, W>(a, degk_smem);
@@ -98,7 +103,8 @@ int main(int argc, char** argv) {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DEGK_BLOCK2, smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-    long long blocks = (N + DEGK_BLOCK2 * W - 1) / (DEGK_BLOCK2 * W);
+    const int per_thread = GEN >= 5 ? 2 * W : W;
+    long long blocks = (N + DEGK_BLOCK2 * per_thread - 1) / (DEGK_BLOCK2 * per_thread);
     const long long resident = (long long)prop.multiProcessorCount * occ;
     if (blocks > resident) blocks = resident;
 
