@@ -24,6 +24,7 @@ from .lowerlevel_solve import Range, get_program, vectorized_asolve, vectorized_
 from .problems import (EnsembleContext, EnsembleProblem, ODEFunction, ODEProblem, ProblemBatch,
                        SDEFunction, SDEProblem, adapt, make_prob_compatible, remake)
 from .solve import EnsembleSolution, ODESolution, solve, solve_host
+from .parallel import EnsembleMoments, MomentsSolution, solve_moments
 
 __all__ = [
     "DegkError", "EnsembleGPUKernel", "GPUEM", "GPUODEAlgorithm", "GPUODEImplicitAlgorithm",
@@ -31,6 +32,6 @@ __all__ = [
     "GPUVern7", "GPUVern9", "alg_order", "Range", "get_program", "vectorized_asolve",
     "vectorized_solve", "EnsembleContext", "EnsembleProblem", "ODEFunction", "ODEProblem",
     "ProblemBatch", "SDEFunction", "SDEProblem", "adapt", "make_prob_compatible", "remake",
-    "EnsembleSolution", "ODESolution", "solve", "solve_host", "models",
+    "EnsembleSolution", "ODESolution", "solve", "solve_host", "models", "EnsembleMoments", "MomentsSolution", "solve_moments",
     "GPUKvaerno3", "GPUKvaerno5", "CallbackSet", "ContinuousCallback", "GPUContinuousCallback", "DiscreteCallback", "GPUDiscreteCallback",
 ]

@@ -125,6 +125,15 @@ def solve(ensembleprob, alg, ensemblealg=None, *, trajectories, batch_size=None,
         raise TypeError("only EnsembleGPUKernel is implemented by this engine")
     if not isinstance(ensembleprob, EnsembleProblem):
         raise TypeError("expected an EnsembleProblem")
+    from .parallel import EnsembleMoments, solve_moments
+    if isinstance(ensembleprob.reduction, EnsembleMoments):
+        # fused ensemble reduction (+ one all-reduce over the ranks of a torchrun job): BASELINE config 5
+        t_start = time.perf_counter()
+        kw = dict(kwargs)
+        dt = kw.pop("dt")
+        sol = solve_moments(ensembleprob, alg, ensemblealg, trajectories=trajectories, dt=dt, batch_size=batch_size,
+                            adaptive=adaptive and not isinstance(ensembleprob.prob, SDEProblem), seed=seed, **kw)
+        return EnsembleSolution(sol, time.perf_counter() - t_start, True)
     if batch_size is None:
         batch_size = trajectories
     if isinstance(ensembleprob.prob, SDEProblem) and seed is not None:

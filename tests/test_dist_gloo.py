@@ -1,6 +1,6 @@
 """world_size-2 gloo test of the multi-GPU host logic (sharding + ensemble-moment all-reduce).
-The per-rank `reduce` partials come from the oracle here (CPU); on the GPU box the same code
-path is fed by degk_solve's reduce output (tests/test_gpu_parity.py)."""
+The per-rank `reduce` partials come from the oracle here (CPU only); on the GPU box the same chain is fed by the
+kernel's reduce output with two ranks (tests/test_moments.py::test_two_rank_moments_fed_by_the_kernel)."""
 import os
 import subprocess
 import sys
