@@ -374,7 +374,9 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.tstops = a->n_tstops > 0 ? a->tstops : nullptr; k.n_tstops = a->tstops ? a->n_tstops : 0;
     k.dt = a->dt; k.abstol = a->abstol; k.reltol = a->reltol;
     k.seed = a->seed; k.reduce = a->reduce; k.totals = (unsigned long long*)a->totals;
-    k.max_iters = a->max_iters > 0 ? a->max_iters : 10000000LL;
+    // adaptive attempts per trajectory are capped (the reference would spin forever on a stalled controller); a
+    // fixed-dt run makes exactly (tf - t0) / dt steps, so it is never cut short unless the caller asks for a cap
+    k.max_iters = a->max_iters > 0 ? a->max_iters : (a->adaptive ? 10000000LL : 0x7fffffffffffffffLL);
     {
         static const int rb = getenv("DEGK_RETIRE_BATCH") ? atoi(getenv("DEGK_RETIRE_BATCH")) : 0;   // tuning knob
         k.retire_batch = rb;

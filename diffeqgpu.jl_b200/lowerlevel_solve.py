@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .julia_ranges import lin_range, step_range
 from .algorithms import (FP_MODES, SCHEDULES, GPUEM, GPUSIEA, GPUODEAlgorithm, GPUSDEAlgorithm)
 from .callbacks import as_callback_set
 from .problems import ODEProblem, ProblemBatch, SDEProblem, adapt
@@ -38,8 +39,7 @@ class Range:
 
     def collect(self, dtype):
         # Tt.(collect(range(Tt(first), Tt(last), length = n)))  (lowerlevel_solve.jl:90-91)
-        a, b = dtype.type(self.start), dtype.type(self.stop)
-        return np.linspace(np.float64(a), np.float64(b), self.length).astype(dtype)
+        return lin_range(dtype.type(self.start), dtype.type(self.stop), self.length, dtype)
 
 
 def _is_number(x):
@@ -55,8 +55,8 @@ def _convert_saveat_fixed(saveat, prob):
         t0, tf = prob.tspan
         if Tt.type(saveat) == Tt.type(0.0):
             return np.array([t0, tf], dtype=Tt)
-        num_points = int(math.ceil(abs(tf - t0) / abs(Tt.type(saveat)))) + 1
-        return np.linspace(np.float64(t0), np.float64(tf), num_points).astype(Tt)
+        num_points = int(math.ceil(abs(Tt.type(tf) - Tt.type(t0)) / abs(Tt.type(saveat)))) + 1
+        return lin_range(Tt.type(t0), Tt.type(tf), num_points, Tt)
     return np.asarray(saveat).astype(Tt).reshape(-1)
 
 
@@ -67,14 +67,28 @@ def _convert_saveat_adaptive(saveat, prob):
         t0, tf = prob.tspan
         if Tt.type(saveat) == Tt.type(0.0):
             return np.array([t0, tf], dtype=Tt)
-        num_points = int(math.ceil(abs(tf - t0) / abs(Tt.type(saveat)))) + 1
+        num_points = int(math.ceil(abs(Tt.type(tf) - Tt.type(t0)) / abs(Tt.type(saveat)))) + 1
         if num_points > MAX_SAVEAT_LENGTH:
             raise ValueError(f"saveat would create too many save points ({num_points}). "
                              "Consider using a larger saveat value.")
-        return np.linspace(np.float64(t0), np.float64(tf), num_points).astype(Tt)
+        return lin_range(Tt.type(t0), Tt.type(tf), num_points, Tt)
     if isinstance(saveat, Range):
         return saveat.collect(Tt)
     return np.asarray(saveat).astype(Tt).reshape(-1)
+
+
+def fixed_dt_rows(Tt, t0, tf, dt, tstops=None):
+    """rows of a fixed-dt, save-every-step run: len = length(t0:dt:tf) [+ length(tstops) - count(x -> x in tstops,
+    timeseries)] (lowerlevel_solve.jl:64-78).  `timeseries` is the Julia range, whose elements are rounded once
+    (julia_ranges.py), not t0 + k*dt: with tspan (0, 1), dt = 0.1 and tstops = [0.3] in Float64 that is 11 rows, not 12."""
+    Tt = np.dtype(Tt)
+    dcode = _lib.F32 if Tt == np.float32 else _lib.F64
+    n_rows = int(_lib.lib().degk_output_rows(dcode, float(t0), float(tf), float(Tt.type(dt)), 0, 1, 0))
+    if tstops is not None:
+        series = step_range(Tt.type(t0), Tt.type(dt), n_rows, Tt)
+        tst = [Tt.type(x) for x in tstops]
+        n_rows += len(tst) - sum(1 for x in series if x in tst)
+    return n_rows
 
 
 def _model_key(f):
@@ -135,7 +149,10 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
     n = prog.info.n_state
     N = len(probs)
     tdt = torch.float32 if prob.dtype == np.float32 else torch.float64
-    with torch.cuda.device(dev):
+    # allocations and the small H2D copies below are ordered on the stream the kernel is launched on (the caller's
+    # `stream` when given): torch's caching allocator ties a block to the stream it was allocated on
+    launch_stream = torch.cuda.current_stream(dev) if stream is None else torch.cuda.ExternalStream(int(stream), device=dev)
+    with torch.cuda.device(dev), torch.cuda.stream(launch_stream):
         # allocate(backend, T, (len, N)) -- lowerlevel_solve.jl:81-83 / 317-323.  ts needs no
         # fill!(ts, t0): the kernel writes t0 into every row it does not reach.
         if layout == "ref":
@@ -177,10 +194,12 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
             a.nreject = out["nreject"].data_ptr(); a.totals = out["totals"].data_ptr()
         a.seed = int(getattr(probs, "seed", 0)) & 0xFFFFFFFFFFFFFFFF
         a.reduce = None if reduce is None else reduce.data_ptr()
-        a.max_iters = int(__import__("os").environ.get("DEGK_MAX_ITERS", "0"))   # 0 => library default (1e9)
+        a.max_iters = int(__import__("os").environ.get("DEGK_MAX_ITERS", "0"))   # 0 => library default (1e7 attempts per trajectory when adaptive, none for fixed dt)
         a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
-        s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
-        prog.solve(a, s)
+        prog.solve(a, launch_stream.cuda_stream)
+        for buf in (probs.u0, probs.p, probs.tspan, reduce):     # inputs made on other streams stay alive until this one is done
+            if isinstance(buf, torch.Tensor) and buf.is_cuda and buf.numel():
+                buf.record_stream(launch_stream)
         # keep inputs alive until the stream has consumed them
         us._degk_keepalive = (probs, d_saveat, d_tstops)
     if stats:
@@ -208,16 +227,7 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
     t0, tf = prob.tspan
     saveat_c = None
     if saveat is None:
-        if save_everystep:
-            # len = length(prob.tspan[1]:dt:prob.tspan[2])  (:71-73, :148-150)
-            n_rows = int(_lib.lib().degk_output_rows(dcode, float(t0), float(tf), float(dt), 0, 1, 0))
-            if tstops is not None:
-                # len += length(tstops) - count(x -> x in tstops, timeseries)  (:74-77)
-                series = {Tt.type(t0) + Tt.type(k) * dt for k in range(n_rows)}
-                tst = [Tt.type(x) for x in tstops]
-                n_rows += len(tst) - sum(1 for x in series if x in tst)
-        else:
-            n_rows = 2
+        n_rows = fixed_dt_rows(Tt, t0, tf, dt, tstops) if save_everystep else 2
     else:
         saveat_c = _convert_saveat_fixed(saveat, prob)
         n_rows = len(saveat_c)

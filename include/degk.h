@@ -194,7 +194,7 @@ typedef struct {
     double* reduce;        /* optional inout [n_rows][n_state][2]: += sum(u), sum(u^2) over the
                               trajectories of this call (SDE kernels; needs tspan_stride == 0) */
     uint64_t* totals;      /* optional inout [4]: += accepted, rejected, failed, 0 */
-    int64_t max_iters;     /* attempts per trajectory before DEGK_RC_MAXITERS; 0 => 1e7 */
+    int64_t max_iters;     /* attempts per trajectory before DEGK_RC_MAXITERS; 0 => 1e7 for adaptive runs, no cap for fixed dt */
     int32_t engine;        /* degk_engine: which adaptive kernel generation to run */
     int32_t reserved;
     const void* tstops;    /* kw `tstops`: n_tstops ascending times of the program's dtype (device pointer in

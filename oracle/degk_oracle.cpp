@@ -854,7 +854,7 @@ void drive(Integ& I, const SolveArgs& a, int order, T t0, T tf, const T* u0, con
         while (I.t < tf && !terminated) {
             I.step_fixed();
             if (!callbacks()) savevalues();
-            if (++iters >= a.max_iters) { I.retcode = RC_MAXITERS; return; }
+            // (no step cap for fixed dt: the run makes exactly (tf - t0) / dt steps, like the reference)
         }
     }
     if (I.t > tf && !has_saveat) {          // kernels.jl:53-57 / :133-137

@@ -94,3 +94,25 @@ def test_shard_range_partitions(n, w):
     assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
     sizes = [hi - lo for lo, hi in parts]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_julia_range_elements_and_tstops_row_count():
+    """range elements must be the ones Julia produces (twice-precision, rounded once): (0:0.1:1)[4] == 0.3.
+    A naive t0 + k*dt in Float64 made tstops on grid points count as extra rows."""
+    from diffeqgpu_b200.julia_ranges import lin_range, step_range
+    from diffeqgpu_b200.lowerlevel_solve import _convert_saveat_adaptive, fixed_dt_rows
+    r = step_range(0.0, 0.1, 11, np.float64)
+    assert r[3] == 0.3 and r[6] == 0.6 and r[7] == 0.7 and r[10] == 1.0
+    assert 0.1 * 3 != 0.3                                  # what the naive grid would have produced
+    assert np.array_equal(lin_range(0.0, 1.0, 11, np.float64), r)
+    assert np.array_equal(step_range(np.float32(0), np.float32(0.1), 101, np.float32)[[3, 100]], np.float32([0.3, 10.0]))
+    assert fixed_dt_rows(np.float64, 0.0, 1.0, 0.1, [0.3]) == 11
+    assert fixed_dt_rows(np.float64, 0.0, 1.0, 0.1, [0.3, 0.6, 0.7]) == 11
+    assert fixed_dt_rows(np.float64, 0.0, 1.0, 0.1, [0.35]) == 12
+    assert fixed_dt_rows(np.float32, 0.0, 1.0, 0.1, [0.3, 0.35]) == 12
+    assert fixed_dt_rows(np.float64, 0.0, 1.0, 0.1) == 11
+    prob = dg.ODEProblem(dg.models.lorenz, np.array([1.0, 0, 0]), (0.0, 1.0), np.array([10.0, 28.0, 8 / 3]))
+    sv = _convert_saveat_adaptive(0.1, prob)               # saveat as a number: range(t0, tf, length = 11)
+    assert sv.dtype == np.float64 and np.array_equal(sv, r)
+    sv = _convert_saveat_adaptive(dg.Range(0.0, 1.0, step=0.1), prob)
+    assert np.array_equal(sv, r)
