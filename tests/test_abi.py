@@ -144,3 +144,27 @@ def test_bindings_mirror_the_header_field_for_field():
         body = re.sub(r"#.*", "", body)
         got = re.findall(r"(\w+)::", body)
         assert got == want, (jname, got, want)
+        # the mirrors are keyword-constructed (Base.@kwdef, a default for every field): a call can only go stale by
+        # naming a field that does not exist -- check every call site
+        assert re.search(r"Base\.@kwdef struct %s\n" % jname, jl), jname
+        assert len(re.findall(r"::[^;=\n]+=", body)) == len(want), (jname, "every field needs a default")
+        calls = re.findall(r"%s\((.*?)\)\)" % jname, jl, re.S)
+        assert calls, jname
+        for call in calls:
+            call = re.sub(r"#.*", "", call)
+            depth, cur, parts = 0, "", []
+            for ch in call:                                   # split the argument list at top-level commas
+                if ch in "([{":
+                    depth += 1
+                if ch in ")]}":
+                    depth -= 1
+                if ch == "," and depth == 0:
+                    parts.append(cur); cur = ""
+                else:
+                    cur += ch
+            parts.append(cur)
+            for part in parts:
+                m = re.match(r"\s*(\w+)\s*=(?!=)", part)
+                assert m, (jname, "positional argument in a constructor call", part.strip()[:60])
+                assert m.group(1) in want, (jname, "unknown field", m.group(1))
+    assert "_convert_saveat" not in jl                        # (round 1 called a function the reference does not have)
