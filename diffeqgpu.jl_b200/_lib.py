@@ -71,7 +71,7 @@ class SolveArgs(C.Structure):
                 ("seed", C.c_uint64), ("reduce", C.c_void_p), ("totals", C.c_void_p),
                 ("max_iters", C.c_int64), ("engine", C.c_int32), ("reserved", C.c_int32),
                 ("tstops", C.c_void_p), ("n_tstops", C.c_int32), ("reserved2", C.c_int32),
-                ("nsaved", C.c_void_p)]
+                ("nsaved", C.c_void_p), ("saveat_stride", C.c_int64)]
 
 
 # every symbol include/degk.h declares (checked by tests/test_abi.py)

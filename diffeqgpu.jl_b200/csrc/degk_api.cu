@@ -341,6 +341,7 @@ static int validate(degk_program* prog, const degk_solve_args* a) {
     if (!(a->dt > 0) && !(a->dt < 0)) { degk_set_error(ctx, "dt must be non-zero"); return DEGK_ERR_INVALID; }
     if (a->saveat && a->n_saveat <= 0) { degk_set_error(ctx, "saveat given with n_saveat <= 0"); return DEGK_ERR_INVALID; }
     if (a->saveat && a->n_rows != a->n_saveat) { degk_set_error(ctx, "n_rows must equal n_saveat when saveat is given"); return DEGK_ERR_INVALID; }
+    if (a->saveat && a->saveat_stride != 0 && a->saveat_stride < a->n_saveat) { degk_set_error(ctx, "saveat_stride must be 0 or >= n_saveat"); return DEGK_ERR_INVALID; }
     if (a->reduce && (!prog->is_sde || a->tspan_stride != 0)) {
         degk_set_error(ctx, "reduce needs an SDE program and a broadcast tspan (tspan_stride == 0)");
         return DEGK_ERR_UNSUPPORTED;
@@ -367,6 +368,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.p = a->p; k.p_stride = a->p_stride;
     k.tspan = a->tspan; k.tspan_stride = a->tspan_stride;
     k.saveat = a->saveat; k.n_saveat = a->saveat ? a->n_saveat : 0;
+    k.saveat_stride = a->saveat ? a->saveat_stride : 0;
     k.save_everystep = a->save_everystep ? 1 : 0;
     k.n_rows = a->n_rows; k.us = a->us; k.ts = a->ts;
     k.out_layout = a->out_layout;
@@ -388,36 +390,17 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     if (!which) sched = DEGK_SCHED_STATIC;
     k.schedule = sched;
 
-    // second-generation adaptive kernel (deferred saves, packed pairs) unless the caller pins v1
-    const bool v2 = which == 1 && a->engine != DEGK_ENGINE_V1 && prog->info.slots_per_thread2 > 0 && !prog->has_events;
+    // the persistent adaptive kernel (degk_ode_kernels4.cuh) unless the caller pins the first generation.  It stages
+    // ONE saveat grid in shared memory: per-problem grids (saveat_stride != 0) and grids longer than
+    // DEGK_SAVEAT_STAGE_MAX run on the first-generation kernel, which reads the grid of its trajectory from global memory
+    const bool stageable = !a->saveat || (a->n_saveat <= DEGK_SAVEAT_STAGE_MAX && a->saveat_stride == 0);
+    const bool v2 = which == 1 && a->engine != DEGK_ENGINE_V1 && prog->info.slots_per_thread2 > 0 && !prog->has_events &&
+                    stageable && (prog->info.is_jit ? prog->jit_fn[2] != nullptr : prog->fn[2] != nullptr);
     if (prog->has_events) sched = k.schedule = DEGK_SCHED_STATIC;   // one thread per trajectory
     const int block = v2 ? DEGK_BLOCK2 : DEGK_BLOCK;
     const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : DEGK_BLOCK;
     size_t smem = 0;
-    void* sv_padded = nullptr;
-    if (v2) {
-        // saveat is staged in shared memory with two +inf sentinels behind it; a grid too long for that gets a
-        // padded copy in device memory for the duration of this launch (stream-ordered allocation)
-        const bool stage = !a->saveat || a->n_saveat <= DEGK_SAVEAT_STAGE_MAX;
-        smem = degk_smem2_bytes(prog, stage && a->saveat ? a->n_saveat : 0);
-        if (!stage) {
-            const size_t es = dtype_size(prog->info.dtype);
-            const size_t nb = (size_t)a->n_saveat * es;
-            CK(ctx, cudaMallocAsync(&sv_padded, nb + 2 * es, stream));
-            CK(ctx, cudaMemcpyAsync(sv_padded, a->saveat, nb, cudaMemcpyDeviceToDevice, stream));
-            CK(ctx, cudaMemsetAsync((char*)sv_padded + nb, 0, 2 * es, stream));
-            // +inf: 0x7f800000 (float) / 0x7ff0000000000000 (double), written bytewise
-            if (es == 4) {
-                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 2, 0x80, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 3, 0x7f, 1, stream));
-                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 6, 0x80, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 7, 0x7f, 1, stream));
-            } else {
-                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 6, 0xf0, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 7, 0x7f, 1, stream));
-                CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 14, 0xf0, 1, stream)); CK(ctx, cudaMemsetAsync((char*)sv_padded + nb + 15, 0x7f, 1, stream));
-            }
-            k.saveat = sv_padded;
-            k.reserved |= 1;
-        }
-    }
+    if (v2) smem = degk_smem2_bytes(prog, a->saveat ? a->n_saveat : 0);
     // fixed-dt kernel, every-step saves in the reference layout: stage R rows per lane in shared
     // memory (<= 48 KB per block, so no opt-in attribute is needed) and flush them coalesced
     // (only when the launch fills the GPU: with a few warps per SM the kernel is latency-bound and the
@@ -454,7 +437,6 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
         cudaError_t e = cudaLaunchKernel(prog->fn[kidx], dim3((unsigned)blocks), dim3((unsigned)block), params, smem, stream);
         if (e != cudaSuccess) { degk_set_error(ctx, "kernel launch failed: %s", cudaGetErrorString(e)); rc = DEGK_ERR_CUDA; }
     }
-    if (sv_padded) cudaFreeAsync(sv_padded, stream);
     return rc;
 }
 
@@ -481,7 +463,7 @@ static int ws_get(degk_ctx* ctx, int s, int slot, size_t bytes, void** out) {
     return DEGK_OK;
 }
 
-enum { WS_U0 = 0, WS_P, WS_TSPAN, WS_US, WS_TS, WS_RC, WS_NA, WS_NR, WS_REDUCE, WS_TOTALS, WS_NSAVED, WS_COUNT };
+enum { WS_U0 = 0, WS_P, WS_TSPAN, WS_US, WS_TS, WS_RC, WS_NA, WS_NR, WS_REDUCE, WS_TOTALS, WS_NSAVED, WS_SAVEAT, WS_COUNT };
 static_assert(WS_COUNT <= DEGK_NWSBUF, "workspace slots");
 
 // Host-side rebuild of the reference's ts array for saveat runs (lowerlevel_solve.jl:318 fill! +
@@ -535,7 +517,7 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
     // broadcast inputs and saveat are uploaded once (stream 0), others per chunk
     cudaStream_t s0 = ctx->streams[0];
     void* d_saveat = nullptr;
-    if (a->saveat) {
+    if (a->saveat && a->saveat_stride == 0) {
         size_t b = es * a->n_saveat;
         if (ctx->saveat_cap < b) {
             if (ctx->d_saveat) CK(ctx, cudaFree(ctx->d_saveat));
@@ -553,7 +535,8 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
     const int ns = std::min(DEGK_NSTREAMS, nchunks);
     // saveat runs of the adaptive generation-2/3 kernels: ts is rebuilt on the host from the
     // per-trajectory row counts instead of being transferred
-    const bool compact_ts = a->ts && a->saveat && a->adaptive && !prog->is_sde && a->engine != DEGK_ENGINE_V1 &&
+    const bool compact_ts = a->ts && a->saveat && a->saveat_stride == 0 && a->n_saveat <= DEGK_SAVEAT_STAGE_MAX &&
+                            a->adaptive && !prog->is_sde && a->engine != DEGK_ENGINE_V1 &&
                             prog->info.slots_per_thread2 > 0 && a->out_layout == DEGK_LAYOUT_REF &&
                             !getenv("DEGK_NO_COMPACT_TS");
     std::thread rebuild_worker;
@@ -596,6 +579,13 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         k.n_traj = cn;
         k.traj_offset = a->traj_offset + c0;
         k.saveat = d_saveat;
+        if (a->saveat && a->saveat_stride != 0) {            // per-problem grids travel with their chunk
+            void* dsv;
+            const size_t b = es * ((size_t)a->saveat_stride * (cn - 1) + a->n_saveat);
+            rc = ws_get(ctx, s, WS_SAVEAT, b, &dsv); if (rc) return rc;
+            CK(ctx, cudaMemcpyAsync(dsv, (const char*)a->saveat + es * a->saveat_stride * c0, b, cudaMemcpyHostToDevice, st));
+            k.saveat = dsv;
+        }
         void *du0, *dp = nullptr, *dts_in, *dus, *dts = nullptr, *drc = nullptr, *dna = nullptr, *dnr = nullptr;
         // inputs
         {

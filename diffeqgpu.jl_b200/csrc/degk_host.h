@@ -11,7 +11,7 @@
 
 #define DEGK_NCOUNTERS 256   // ring of work-queue counters (one per in-flight adaptive launch)
 #define DEGK_NSTREAMS 3      // streams used by degk_solve_host to overlap H2D / solve / D2H
-#define DEGK_NWSBUF 12
+#define DEGK_NWSBUF 13
 
 namespace degk { struct KArgs; }
 

@@ -361,7 +361,11 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
         src += std::string("template <class T_, class M_> using METHODT = ") + method_template(d->alg) + ";\n";
         src += "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_fixed(const degk::KArgs a) {\n"
                "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
-               "    degk::ode_solve_body<REAL, MODEL, METHOD>(a, degk_smem);\n}\n";   // (the first-generation adaptive kernel exists ahead of time only, for A/B runs)
+               "    degk::ode_solve_body<REAL, MODEL, METHOD>(a, degk_smem);\n}\n"
+               // first-generation adaptive kernel (one thread per trajectory, saveat read from global memory): runs
+               // per-problem saveat grids and grids too long for shared memory
+               "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_adaptive(const degk::KArgs a) {\n"
+               "    degk::ode_asolve_body<REAL, MODEL, METHOD>(a);\n}\n";
         snprintf(buf, sizeof buf,
                  "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
                  "extern \"C\" __global__ void __launch_bounds__(%d, (degk::asolve4_minblocks<REAL, METHOD>())) degk_jit_adaptive2(const degk::KArgs a) {\n"
@@ -450,7 +454,6 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     const bool is_sde = prog->is_sde;
     CUfunction f0 = nullptr, f1 = nullptr;
     DRV(ctx, g_drv.ModuleGetFunction(&f0, mod, "degk_jit_fixed"));
-    // f1 (first-generation adaptive kernel) is not part of JIT builds
     prog->jit_fn[0] = f0;
     prog->jit_fn[1] = f1;
     const bool events = d->events != 0 || d->n_callbacks > 0 || d->n_ccallbacks > 0;
@@ -460,6 +463,8 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
         DRV(ctx, g_drv.ModuleGetFunction(&f1, mod, "degk_jit_adaptive"));
         prog->jit_fn[1] = f1;
     } else if (!is_sde) {
+        DRV(ctx, g_drv.ModuleGetFunction(&f1, mod, "degk_jit_adaptive"));
+        prog->jit_fn[1] = f1;
         DRV(ctx, g_drv.ModuleGetFunction(&f2, mod, "degk_jit_adaptive2"));
     }
     prog->jit_fn[2] = f2;

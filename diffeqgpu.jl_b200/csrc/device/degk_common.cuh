@@ -58,6 +58,8 @@ struct KArgs {
     const void* tstops;  // event-capable kernels (degk_ode_events.cuh): times the steppers must hit
     int n_tstops;
     int stage_rows;      // fixed-dt kernel: rows staged in shared memory per lane before a coalesced flush (0 = off)
+    i64 saveat_stride;   // elements between the saveat grids of two trajectories; 0 = one grid shared by all
+                         // (per-problem `saveat` of the reference, kernels.jl:15-17, 89-91: same length everywhere)
 };
 
 // ---- fused multiply-add that stays fused in both fp modes (reference: @muladd / muladd) ----

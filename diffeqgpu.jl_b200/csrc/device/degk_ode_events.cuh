@@ -187,8 +187,8 @@ DEGK_DEV void ode_solve_events_body(const KArgs& a) {
         T t0, tf;
         load_problem<T, Model>(a, traj, u, p, t0, tf);
         const T dt = (T)a.dt;                // integ.dt: the nominal step, also when a tstop shortens one (Q4)
-        const T* saveat = (const T*)a.saveat;
-        const bool has_saveat = saveat != nullptr;
+        const bool has_saveat = a.saveat != nullptr;
+        const T* saveat = (const T*)a.saveat + (has_saveat ? traj * a.saveat_stride : 0);      // this trajectory's grid
         typename Method::Keep K;
         int cur = 0;                 // 1-based index of the next saveat entry
         i64 step_idx = 1;            // 0-based row of the next every-step save
@@ -316,8 +316,8 @@ DEGK_DEV void ode_asolve_events_body(const KArgs& a) {
         T p[Model::NP > 0 ? Model::NP : 1];
         T t0, tf;
         load_problem<T, Model>(a, traj, u, p, t0, tf);
-        const T* saveat = (const T*)a.saveat;
-        const bool has_saveat = saveat != nullptr;
+        const bool has_saveat = a.saveat != nullptr;
+        const T* saveat = (const T*)a.saveat + (has_saveat ? traj * a.saveat_stride : 0);      // this trajectory's grid
         typename Method::Keep K;
         int cur = 0;
         if (has_saveat) {            // kernels.jl:116-126

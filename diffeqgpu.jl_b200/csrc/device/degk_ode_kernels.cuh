@@ -44,8 +44,8 @@ DEGK_DEV void ode_solve_body(const KArgs& a, unsigned char* smem_raw) {
     T p[Model::NP > 0 ? Model::NP : 1];
     T t0 = (T)0, tf = (T)0;
     const T dt = (T)a.dt;
-    const T* saveat = (const T*)a.saveat;
-    const bool has_saveat = saveat != nullptr;
+    const bool has_saveat = a.saveat != nullptr;
+    const T* saveat = (const T*)a.saveat + (has_saveat && valid ? traj * a.saveat_stride : 0);   // this trajectory's grid
     typename Method::Keep K;
     int cur = 0;                 // 1-based index of the next saveat entry
     i64 step_idx = 1;            // 0-based row of the next every-step save
@@ -176,7 +176,7 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
     constexpr int N = Model::N;
     typedef Ctl<T, Method::ORDER> C;
     const T abstol = (T)a.abstol, reltol = (T)a.reltol;
-    const T* saveat = (const T*)a.saveat;
+    const T* saveat = (const T*)a.saveat;              // re-pointed at the trajectory's own grid when it is claimed
     const bool has_saveat = saveat != nullptr;
     const u32 lane = lane_id();
     const u32 lt_mask = (1u << lane) - 1u;
@@ -228,6 +228,7 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                 // kernels.jl:116-126
                 cur = 0;
                 if (has_saveat) {
+                    saveat = (const T*)a.saveat + traj * a.saveat_stride;
                     cur = 1;
                     if (t0 == saveat[0]) {
                         cur = 2;

@@ -102,8 +102,8 @@ DEGK_DEV void sde_solve_body(const KArgs& a) {
     load_problem<T, Model>(a, tl, u, p, t0, tf);
     const T dt = (T)a.dt;
     const T sqdt = sqrt_(dt);
-    const T* saveat = (const T*)a.saveat;
-    const bool has_saveat = saveat != nullptr;
+    const bool has_saveat = a.saveat != nullptr;
+    const T* saveat = (const T*)a.saveat + (has_saveat ? tl * a.saveat_stride : 0);            // this trajectory's grid
     const bool red = a.reduce != nullptr;
     const u64 gid = (u64)(a.traj_offset + tl);
     const u32 k0 = (u32)a.seed, k1 = (u32)(a.seed >> 32);

@@ -50,6 +50,7 @@ Base.@kwdef struct SolveArgs
     max_iters::Int64 = 0; engine::Int32 = 0; reserved::Int32 = 0
     tstops::CuPtr{Cvoid} = CU_NULL; n_tstops::Int32 = 0; reserved2::Int32 = 0
     nsaved::CuPtr{Int32} = CU_NULL
+    saveat_stride::Int64 = 0                                  # per-problem saveat grids (kernels.jl:15-17): elements between two grids
 end
 
 alg_id(::GPUTsit5) = 0; alg_id(::GPUVern7) = 1; alg_id(::GPUVern9) = 2

@@ -162,7 +162,11 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
             ts = torch.empty((n_rows, N), dtype=tdt, device=dev)
             us = torch.empty((n_rows, n, N), dtype=tdt, device=dev)
         d_saveat = None
-        if saveat is not None:
+        sv_stride = 0
+        if getattr(probs, "saveat", None) is not None:
+            d_saveat = probs.saveat                   # (N, nsave): every trajectory reads its own grid
+            sv_stride = int(d_saveat.shape[1])
+        elif saveat is not None:
             d_saveat = torch.as_tensor(saveat, dtype=tdt).to(dev)
         out = {}
         if stats:
@@ -179,7 +183,9 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
         a.dt = float(prob.dtype.type(dt))
         a.adaptive = int(adaptive)
         a.abstol = float(prob.dtype.type(abstol)); a.reltol = float(prob.dtype.type(reltol))
-        a.saveat = _ptr(d_saveat); a.n_saveat = 0 if saveat is None else len(saveat)
+        a.saveat = _ptr(d_saveat)
+        a.n_saveat = sv_stride if sv_stride else (0 if saveat is None else len(saveat))
+        a.saveat_stride = sv_stride
         d_tstops = None
         if tstops is not None and len(tstops):
             d_tstops = torch.as_tensor(np.asarray(tstops, dtype=prob.dtype), dtype=tdt).to(dev)   # adapt(backend, tstops)
@@ -225,8 +231,14 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
     dt = Tt.type(dt)
     dcode = _lib.F32 if Tt == np.float32 else _lib.F64
     t0, tf = prob.tspan
+    if not isinstance(probs, ProblemBatch):
+        probs = adapt("cuda", probs)
     saveat_c = None
-    if saveat is None:
+    inner = getattr(probs, "saveat", None)
+    if inner is not None:                       # saveat = _saveat === nothing ? saveat : _saveat  (kernels.jl:15-17)
+        saveat_c = np.zeros(int(inner.shape[1]), dtype=Tt)
+        n_rows = int(inner.shape[1])
+    elif saveat is None:
         n_rows = fixed_dt_rows(Tt, t0, tf, dt, tstops) if save_everystep else 2
     else:
         saveat_c = _convert_saveat_fixed(saveat, prob)
@@ -250,7 +262,12 @@ def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save
     dt = Tt.type(dt)
     dcode = _lib.F32 if Tt == np.float32 else _lib.F64
     t0, tf = prob.tspan
+    if not isinstance(probs, ProblemBatch):
+        probs = adapt("cuda", probs)
     saveat_c = None if saveat is None else _convert_saveat_adaptive(saveat, prob)
+    inner = getattr(probs, "saveat", None)
+    if inner is not None:                       # the problems' own grids take precedence (kernels.jl:89-91)
+        saveat_c = np.zeros(int(inner.shape[1]), dtype=Tt)
     if saveat_c is None:
         # len = ceil(Int, (tf - t0)/dt) + 1 when save_everystep else 2  (:311-316).  Only the
         # first row (+ nothing else) is ever written in the save_everystep case.

@@ -204,11 +204,14 @@ class ProblemBatch:
     as torch CUDA tensors.  Reference: `adapt(dev, adapt.((dev,), probs))`, src/solve.jl:399-400.
     """
 
-    def __init__(self, prob, u0, p, tspan, n_traj, seed=0):
+    def __init__(self, prob, u0, p, tspan, n_traj, seed=0, saveat=None):
         self.prob = prob
         self.u0, self.p, self.tspan = u0, p, tspan
         self.n_traj = int(n_traj)
         self.seed = int(seed)
+        # per-problem saveat grids, (N, nsave) -- `ODEProblem(...; saveat = ...)` carried in prob.kwargs by the reference
+        # (kernels.jl:15-17, 89-91); all of the same length (src/solve.jl:226-245).  None: the solver's `saveat` keyword
+        self.saveat = saveat
 
     def __len__(self):
         return self.n_traj
@@ -218,7 +221,7 @@ class ProblemBatch:
         return self.u0.device
 
     @staticmethod
-    def from_arrays(prob, *, u0=None, p=None, tspan=None, n_traj=None, device="cuda", seed=None):
+    def from_arrays(prob, *, u0=None, p=None, tspan=None, n_traj=None, device="cuda", seed=None, saveat=None):
         """Build a batch directly from arrays (no per-trajectory Python objects).
         Each of u0/p/tspan may be None (use the prototype's value, broadcast) or an array with
         a leading trajectory axis."""
@@ -250,7 +253,12 @@ class ProblemBatch:
             raise ValueError("u0/p/tspan disagree on the number of trajectories")
         if seed is None:
             seed = getattr(prob, "seed", 0)
-        return ProblemBatch(prob, u0_t, p_t, ts_t, n_traj, seed)
+        sv_t = None
+        if saveat is not None:
+            sv_t = torch.as_tensor(np.ascontiguousarray(saveat)).to(device=dev, dtype=dt).contiguous()
+            if sv_t.ndim != 2 or sv_t.shape[0] != n_traj:
+                raise ValueError("per-problem saveat must have shape (N, nsave): grids of the same length for every trajectory")
+        return ProblemBatch(prob, u0_t, p_t, ts_t, n_traj, seed, sv_t)
 
     @staticmethod
     def from_problems(probs: Sequence, device="cuda"):
@@ -262,8 +270,16 @@ class ProblemBatch:
         p = np.stack([pr.p for pr in probs]) if proto.p.size else None
         ts = np.array([pr.tspan for pr in probs], dtype=proto.dtype)
         same_t = bool((ts == ts[0]).all())
+        # inner saveat (prob.kwargs[:saveat]): all problems or none, and all of the same length -- src/solve.jl:226-245
+        svs = [pr.kwargs.get("saveat") for pr in probs]
+        saveat = None
+        if any(sv is not None for sv in svs):
+            if any(sv is None for sv in svs) or len({np.size(sv) for sv in svs}) != 1:
+                raise ValueError("Using different saveat in EnsembleGPUKernel requires all of them to be of same length. "
+                                 "Use saveats of same size only.")
+            saveat = np.stack([np.asarray(sv, dtype=proto.dtype).reshape(-1) for sv in svs])
         return ProblemBatch.from_arrays(proto, u0=u0, p=p, tspan=None if same_t else ts,
-                                        n_traj=len(probs), device=device)
+                                        n_traj=len(probs), device=device, saveat=saveat)
 
 
 def adapt(device, probs):

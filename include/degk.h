@@ -207,6 +207,10 @@ typedef struct {
                               hold ts = saveat[k], the others keep t0 -- which lets a caller pass
                               ts = NULL and rebuild the reference's ts array from 4 bytes per
                               trajectory instead of transferring it (degk_solve_host does) */
+    int64_t saveat_stride; /* elements between the saveat grids of consecutive trajectories; 0 = one grid for all.
+                              Per-problem `saveat` (reference kernels.jl:15-17, 89-91, src/solve.jl:226-250): every
+                              trajectory brings its own grid of the SAME length n_saveat; `saveat` then points at
+                              n_traj * saveat_stride values */
 } degk_solve_args;
 
 DEGK_API int degk_version(void);

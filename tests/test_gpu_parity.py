@@ -350,6 +350,53 @@ def test_soa_layout_equals_ref_layout(dg):
     assert np.array_equal(a["us"], b["us"].transpose(2, 0, 1))
 
 
+@pytest.mark.parametrize("adaptive", [True, False])
+def test_per_problem_saveat(dg, adaptive):
+    """`ODEProblem(...; saveat = ...)` per problem (reference kernels.jl:15-17, 89-91, src/solve.jl:226-250): every
+    trajectory is saved on its own grid (same length everywhere) and the problems' grids take precedence over the
+    solver keyword.  Checked against shared-grid runs of the two halves; also through the list-of-problems path, for
+    the NVRTC program and for a grid that is too long to stage in shared memory."""
+    import torch
+    n = 600
+    p = lorenz_sweep(n, seed=8)
+    ga, gb = np.array([0.0, 0.5, 1.0, 2.0], f32), np.array([0.25, 0.75, 1.5, 2.0], f32)
+    grids = np.where((np.arange(n) % 2 == 0)[:, None], ga, gb).astype(f32)
+    prob = dg.ODEProblem(dg.models.lorenz, U0_LORENZ.astype(f32), (0.0, 2.0), P0_LORENZ.astype(f32))
+    kw = dict(dt=f32(0.01), fp_mode="strict")
+    if adaptive:
+        kw.update(abstol=f32(1e-6), reltol=f32(1e-6))
+    solve = dg.vectorized_asolve if adaptive else dg.vectorized_solve
+
+    def run(pp, func=dg.models.lorenz, **k2):
+        pr = dg.ODEProblem(func, U0_LORENZ.astype(f32), (0.0, 2.0), P0_LORENZ.astype(f32))
+        b = dg.ProblemBatch.from_arrays(pr, p=pp, device="cuda:0", **{k: v for k, v in k2.items() if k == "saveat"})
+        ts, us = solve(b, pr, dg.GPUTsit5(), **kw, **{k: v for k, v in k2.items() if k != "saveat"})
+        torch.cuda.synchronize()
+        return ts.cpu().numpy(), us.cpu().numpy()
+    ts, us = run(p, saveat=grids)
+    for sel, g in ((np.arange(n) % 2 == 0, ga), (np.arange(n) % 2 == 1, gb)):
+        ts1, us1 = solve(dg.ProblemBatch.from_arrays(prob, p=p[sel], device="cuda:0"), prob, dg.GPUTsit5(), saveat=g, **kw)
+        torch.cuda.synchronize()
+        assert np.array_equal(ts[sel], ts1.cpu().numpy()) and np.array_equal(us[sel], us1.cpu().numpy())
+    # list of problems carrying their own saveat (the solver keyword is overridden), and the NVRTC program
+    probs = [dg.ODEProblem(dg.models.lorenz, U0_LORENZ.astype(f32), (0.0, 2.0), p[i], kwargs=dict(saveat=grids[i])) for i in range(64)]
+    ts2, us2 = solve(probs, prob, dg.GPUTsit5(), saveat=np.array([9.0, 9.0, 9.0, 9.0], f32), **kw)
+    torch.cuda.synchronize()
+    assert np.array_equal(ts2.cpu().numpy(), ts[:64]) and np.array_equal(us2.cpu().numpy(), us[:64])
+    ts3, us3 = run(p[:64], func=dg.models.lorenz_src, saveat=grids[:64])
+    assert np.array_equal(ts3, ts[:64]) and np.array_equal(us3, us[:64])
+    with pytest.raises(ValueError):
+        dg.ProblemBatch.from_problems([probs[0], dg.ODEProblem(dg.models.lorenz, U0_LORENZ.astype(f32), (0.0, 2.0), p[1],
+                                                               kwargs=dict(saveat=np.array([0.5], f32)))], device="cuda:0")
+    if adaptive:
+        # a grid longer than the kernel's shared-memory staging limit runs on the per-thread engine: same values
+        long = np.linspace(0, 2, 6001).astype(f32)
+        tl, ul = solve(dg.ProblemBatch.from_arrays(prob, p=p[:40], device="cuda:0"), prob, dg.GPUTsit5(), saveat=long, **kw)
+        ts4, us4 = solve(dg.ProblemBatch.from_arrays(prob, p=p[:40], device="cuda:0"), prob, dg.GPUTsit5(), saveat=long[::3], **kw)
+        torch.cuda.synchronize()
+        assert np.array_equal(tl.cpu().numpy()[:, ::3], ts4.cpu().numpy()) and np.array_equal(ul.cpu().numpy()[:, ::3], us4.cpu().numpy())
+
+
 def test_dt_less_than_min_reported_per_trajectory(dg, oracle):
     g = gpu_solve(dg, "lorenz", "tsit5", U0_LORENZ, lorenz_sweep(64, f64), [0, 1], dt=1e-15, adaptive=True,
                   save_everystep=False, dtype=f64)
