@@ -20,7 +20,7 @@ SCHED_STATIC, SCHED_QUEUE, SCHED_AUTO = 0, 1, 2
 NOISE_NONE, NOISE_DIAGONAL, NOISE_GENERAL = 0, 1, 2
 ENGINE_AUTO, ENGINE_V1 = 0, 1
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
-            5: "Singular", 6: "Terminated"}
+            5: "Singular", 6: "Terminated", 7: "InitialFailure"}
 
 
 class DegkError(RuntimeError):
@@ -69,9 +69,9 @@ class SolveArgs(C.Structure):
                 ("out_layout", C.c_int32), ("schedule", C.c_int32),
                 ("retcode", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p),
                 ("seed", C.c_uint64), ("reduce", C.c_void_p), ("totals", C.c_void_p),
-                ("max_iters", C.c_int64), ("engine", C.c_int32), ("reserved", C.c_int32),
+                ("max_iters", C.c_int64), ("engine", C.c_int32), ("dae_init", C.c_int32),
                 ("tstops", C.c_void_p), ("n_tstops", C.c_int32), ("reserved2", C.c_int32),
-                ("nsaved", C.c_void_p), ("saveat_stride", C.c_int64)]
+                ("nsaved", C.c_void_p), ("saveat_stride", C.c_int64), ("order", C.c_void_p)]
 
 
 # every symbol include/degk.h declares (checked by tests/test_abi.py)

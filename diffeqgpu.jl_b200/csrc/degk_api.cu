@@ -351,6 +351,10 @@ static int validate(degk_program* prog, const degk_solve_args* a) {
         return DEGK_ERR_INVALID;
     }
     if (a->out_layout != DEGK_LAYOUT_REF && a->out_layout != DEGK_LAYOUT_SOA) { degk_set_error(ctx, "bad out_layout"); return DEGK_ERR_INVALID; }
+    if (a->dae_init && prog->has_events) {
+        degk_set_error(ctx, "dae_init is not available for programs built with tstops / callbacks");
+        return DEGK_ERR_UNSUPPORTED;
+    }
     if (a->tstops && a->n_tstops > 0 && !prog->has_events) {
         degk_set_error(ctx, "tstops need a program built with degk_model_desc.events = 1");
         return DEGK_ERR_UNSUPPORTED;
@@ -369,6 +373,8 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     k.tspan = a->tspan; k.tspan_stride = a->tspan_stride;
     k.saveat = a->saveat; k.n_saveat = a->saveat ? a->n_saveat : 0;
     k.saveat_stride = a->saveat ? a->saveat_stride : 0;
+    k.order = a->order;
+    if (a->dae_init) k.reserved |= 2;
     k.save_everystep = a->save_everystep ? 1 : 0;
     k.n_rows = a->n_rows; k.us = a->us; k.ts = a->ts;
     k.out_layout = a->out_layout;
@@ -576,6 +582,7 @@ extern "C" int degk_solve_host(degk_program* prog, const degk_solve_args* a, int
         const int64_t c0 = (int64_t)c * chunk_traj;
         const int64_t cn = std::min<int64_t>(chunk_traj, N - c0);
         degk_solve_args k = *a;
+        k.order = nullptr;                     // (a start order refers to device memory of the whole batch)
         k.n_traj = cn;
         k.traj_offset = a->traj_offset + c0;
         k.saveat = d_saveat;

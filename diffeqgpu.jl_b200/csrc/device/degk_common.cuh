@@ -60,6 +60,9 @@ struct KArgs {
     int stage_rows;      // fixed-dt kernel: rows staged in shared memory per lane before a coalesced flush (0 = off)
     i64 saveat_stride;   // elements between the saveat grids of two trajectories; 0 = one grid shared by all
                          // (per-problem `saveat` of the reference, kernels.jl:15-17, 89-91: same length everywhere)
+    const int* order;    // optional: the k-th trajectory the adaptive kernel starts is order[k] (a permutation of
+                         // 0..n_traj-1, e.g. sorted by a parameter so that a warp's trajectories take similar numbers
+                         // of steps); outputs stay at the trajectory's own index
 };
 
 // ---- fused multiply-add that stays fused in both fp modes (reference: @muladd / muladd) ----

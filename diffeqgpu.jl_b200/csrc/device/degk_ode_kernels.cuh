@@ -22,6 +22,7 @@
 //    sectors are merged in the 126 MB L2 before they are written back.
 #pragma once
 #include "degk_common.cuh"
+#include "degk_dae_init.cuh"
 
 namespace degk {
 
@@ -80,21 +81,31 @@ DEGK_DEV void ode_solve_body(const KArgs& a, unsigned char* smem_raw) {
         nbuf = 0;
         __syncwarp();
     };
+    bool init_failed = false;
     if (valid) {
         load_problem<T, Model>(a, traj, u, p, t0, tf);
-        // kernels.jl:34-47
-        if (has_saveat) {
+        // DAE initialisation (kernels.jl:19-25: SimpleTrustRegion, tolerances 1e-6); row 1 of the every-step path
+        // is prob.u0, the saveat path stores the initialised value (kernels.jl:40 vs :44)
+        T u_given[N];
+        DEGK_UNROLL for (int c = 0; c < N; ++c) u_given[c] = u[c];
+        if (a.reserved & 2) init_failed = !dae_initialize<T, Model>(u, p, t0, (T)1.0e-6, (T)1.0e-6);
+        if (init_failed) {                       // kernels.jl:63-70: store the initial values and bail out
+            store_u<T, N>(a, traj, 0, u_given); store_t<T>(a, traj, 0, t0);
+            ts_written = 1; cur = 2;
+            if (!has_saveat && !a.save_everystep) { store_u<T, N>(a, traj, 1, u_given); store_t<T>(a, traj, 1, t0); ts_written = 2; }
+            rc = RC_INIT_FAILURE; ++nfail;
+        } else if (has_saveat) {                 // kernels.jl:34-47
             cur = 1;
             if (t0 == saveat[0]) { cur = 2; store_u<T, N>(a, traj, 0, u); store_t<T>(a, traj, 0, t0); }
         } else {
             store_t<T>(a, traj, 0, t0);
-            store_u<T, N>(a, traj, 0, u);
+            store_u<T, N>(a, traj, 0, u_given);
             ts_written = 1;
         }
         Method::init(K, u, p, t0);
         t = t0; tprev = t0;
     }
-    bool active = valid && (t < tf);
+    bool active = valid && !init_failed && (t < tf);
     while (__any_sync(0xffffffffu, active)) {
         if (active) {
             if (!first) Method::accepted(K);     // FSAL shift deferred so the last step's
@@ -221,6 +232,23 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                 claim = a.n_traj;
                 have = true;
                 load_problem<T, Model>(a, traj, u, p, t0, tf);
+                bool init_ok = true;
+                if (a.reserved & 2) {                    // kernels.jl:93-99 (tolerances of the solve)
+                    T u_given[N];
+                    DEGK_UNROLL for (int c = 0; c < N; ++c) u_given[c] = u[c];
+                    init_ok = dae_initialize<T, Model>(u, p, t0, abstol, reltol);
+                    if (!init_ok) {                      // kernels.jl:143-150
+                        store_u<T, N>(a, traj, 0, u_given); store_t<T>(a, traj, 0, t0);
+                        if (!has_saveat && !a.save_everystep) { store_u<T, N>(a, traj, 1, u_given); store_t<T>(a, traj, 1, t0); }
+                        fill_unwritten_ts<T>(a, traj, (!has_saveat && !a.save_everystep) ? 2 : 1, t0);
+                        if (a.retcode) a.retcode[traj] = RC_INIT_FAILURE;
+                        if (a.naccept) a.naccept[traj] = 0;
+                        if (a.nreject) a.nreject[traj] = 0;
+                        ++tot_fail;
+                        have = false;
+                    }
+                }
+                if (init_ok) {
                 t = t0;
                 h = (T)a.dt;
                 qold = C::qoldinit();
@@ -249,6 +277,7 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                     if (a.nreject) a.nreject[traj] = 0;
                     have = false;
                 }
+                }   // init_ok
             }
             if (__all_sync(0xffffffffu, !have)) {
                 if (exhausted) break;

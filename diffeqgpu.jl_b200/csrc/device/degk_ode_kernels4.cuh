@@ -25,6 +25,7 @@
 //        - save records of the packed build are replayed two per lane with the packed stepper.
 #pragma once
 #include "degk_ode_kernels3.cuh"
+#include "degk_dae_init.cuh"
 
 #ifndef DEGK4_HK
 #define DEGK4_HK 1          // h-scaled stage sums in the fast build
@@ -294,18 +295,37 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
     // and trajectories with nothing to integrate (empty span, non-finite data, dt0 that cannot start).
     auto load_pool = [&](i64 base, int n) {
         if ((int)lane < n) {
-            const i64 claim = base + lane;
+            const i64 claim = a.order ? (i64)a.order[base + lane] : base + lane;
             T us_[N], ps_[NPA], t0_, tf_;
             load_problem<T, Model>(a, claim, us_, ps_, t0_, tf_);
             int c1 = 1;
-            if (has_saveat) {
+            bool init_ok = true;
+            if (a.reserved & 2) {                            // DAE initialisation, kernels.jl:93-99 (tolerances of the solve)
+                T ug[N];
+                DEGK_UNROLL for (int c = 0; c < N; ++c) ug[c] = us_[c];
+                init_ok = dae_initialize<T, Model>(us_, ps_, t0_, abstol, reltol);
+                if (!init_ok) {                              // kernels.jl:143-150: store the initial values and bail out
+                    store_u<T, N>(a, claim, 0, ug); store_t<T>(a, claim, 0, t0_);
+                    const bool ends = !has_saveat && !a.save_everystep;
+                    if (ends) { store_u<T, N>(a, claim, 1, ug); store_t<T>(a, claim, 1, t0_); }
+                    if (a.ts != nullptr) for (i64 k = ends ? 2 : 1; k < a.n_rows; ++k) store_t<T>(a, claim, k, t0_);
+                    if (a.retcode) a.retcode[claim] = RC_INIT_FAILURE;
+                    if (a.naccept) a.naccept[claim] = 0;
+                    if (a.nreject) a.nreject[claim] = 0;
+                    if (has_saveat && a.nsaved) a.nsaved[claim] = 1;
+                    ++tot_fail;
+                }
+            }
+            if (!init_ok) {
+                c1 = 0;
+            } else if (has_saveat) {
                 if (t0_ == save_time(1)) { c1 = 2; store_u<T, N>(a, claim, 0, us_); store_t<T>(a, claim, 0, t0_); }
                 if (a.ts != nullptr) for (i64 k = c1 - 1; k < a.n_rows; ++k) store_t<T>(a, claim, k, t0_);
             } else {
                 store_u<T, N>(a, claim, 0, us_);
                 if (a.ts != nullptr) for (i64 k = 0; k < a.n_rows; ++k) store_t<T>(a, claim, k, t0_);
             }
-            if (!(t0_ < tf_)) {                          // empty time span: nothing to integrate
+            if (init_ok && !(t0_ < tf_)) {               // empty time span: nothing to integrate
                 if (!has_saveat && !a.save_everystep) { store_u<T, N>(a, claim, 1, us_); store_t<T>(a, claim, 1, t0_); }
                 if (a.retcode) a.retcode[claim] = RC_SUCCESS;
                 if (a.naccept) a.naccept[claim] = 0;
@@ -336,7 +356,7 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
         cur[s] = c1;
         next_save[s] = save_time(c1);
         next_save2[s] = save_time(c1 + 1);
-        traj[s] = pool_base + ei;
+        traj[s] = a.order ? a.order[pool_base + ei] : pool_base + ei;
         const T h0 = (T)a.dt;
         // dt0 < dtmin errors at the first attempt; non-finite time data cannot be integrated:
         // both park the slot (dead), the retire path derives the return code

@@ -139,7 +139,7 @@ def _ptr(t):
 
 def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_everystep, n_rows,
             fp_mode, schedule, layout, stats, stream, traj_offset=0, reduce=None, engine="auto",
-            callback=None, tstops=None):
+            callback=None, tstops=None, sort_by=None):
     if not isinstance(probs, ProblemBatch):
         probs = adapt("cuda", probs)
     dev = probs.device
@@ -200,14 +200,22 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
             a.nreject = out["nreject"].data_ptr(); a.totals = out["totals"].data_ptr()
         a.seed = int(getattr(probs, "seed", 0)) & 0xFFFFFFFFFFFFFFFF
         a.reduce = None if reduce is None else reduce.data_ptr()
+        d_order = None
+        if sort_by is not None and adaptive:
+            # start order of the trajectories: sorted by a key that predicts the step count (north_star (5): "optional
+            # sorting of trajectories by parameter").  `sort_by`: int = column of p, or a length-N tensor / array of keys
+            key = probs.p[:, int(sort_by)] if isinstance(sort_by, (int, np.integer)) else torch.as_tensor(sort_by).to(dev)
+            d_order = torch.argsort(key.reshape(-1)).to(torch.int32)
+            a.order = d_order.data_ptr()
         a.max_iters = int(__import__("os").environ.get("DEGK_MAX_ITERS", "0"))   # 0 => library default (1e7 attempts per trajectory when adaptive, none for fixed dt)
         a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
+        a.dae_init = int(bool(getattr(prob.f, "initialize", False))) if isinstance(prob, ODEProblem) else 0
         prog.solve(a, launch_stream.cuda_stream)
         for buf in (probs.u0, probs.p, probs.tspan, reduce):     # inputs made on other streams stay alive until this one is done
             if isinstance(buf, torch.Tensor) and buf.is_cuda and buf.numel():
                 buf.record_stream(launch_stream)
         # keep inputs alive until the stream has consumed them
-        us._degk_keepalive = (probs, d_saveat, d_tstops)
+        us._degk_keepalive = (probs, d_saveat, d_tstops, d_order)
     if stats:
         return ts, us, out
     return ts, us
@@ -252,7 +260,7 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
 def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save_everystep=False,
                       abstol=np.float32(1e-6), reltol=np.float32(1e-3), debug=False, callback=None,
                       tstops=None, fp_mode="strict", schedule="auto", layout="ref", stats=False,
-                      stream=None, engine="auto", **kwargs):
+                      stream=None, engine="auto", sort_by=None, **kwargs):
     """Adaptive batched solve (defaults as lowerlevel_solve.jl:253-260)."""
     if isinstance(prob, SDEProblem):
         raise RuntimeError("Adaptive time-stepping is not supported yet with GPUEM.")   # :348-356
@@ -278,4 +286,4 @@ def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save
     return _launch(probs, prob, alg, dt=dt, adaptive=True, abstol=abstol, reltol=reltol,
                    saveat=saveat_c, save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
                    schedule=schedule, layout=layout, stats=stats, stream=stream, engine=engine,
-                   callback=callback, tstops=tstops)
+                   callback=callback, tstops=tstops, sort_by=sort_by)

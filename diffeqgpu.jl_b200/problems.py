@@ -38,6 +38,8 @@ class ODEFunction:
     force_jit: bool = False
     mass_matrix: Optional[str] = None   # body assigning Mm[i][j] of a constant mass matrix (stiff solvers), None = identity
     use_jac: bool = True      # False: ignore the analytic Jacobian (the function "has no jac"), for the AD / FD paths
+    initialize: bool = False  # mass-matrix DAE: solve the algebraic equations for consistent initial values before the first
+                              # step (the reference does when the function carries initialization data, kernels.jl:19-25)
 
     def __post_init__(self):
         if self.builtin is None and self.rhs is None:

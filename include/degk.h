@@ -87,7 +87,8 @@ typedef enum {
     DEGK_RC_UNSTABLE = 3,         /* non-finite state or step size */
     DEGK_RC_MAXITERS = 4,
     DEGK_RC_SINGULAR = 5,         /* reference: SingularException, linalg/lu.jl:41-44 */
-    DEGK_RC_TERMINATED = 6        /* terminate!(integrator) in a callback affect, integrator_utils.jl:52-66 */
+    DEGK_RC_TERMINATED = 6,       /* terminate!(integrator) in a callback affect, integrator_utils.jl:52-66 */
+    DEGK_RC_INIT_FAILURE = 7      /* DAE initialisation did not converge (dae_init; kernels.jl:63-70, 143-150) */
 } degk_retcode;
 
 /* DEGK_ENGINE_AUTO picks the second-generation adaptive kernel (batched deferred saves, two
@@ -196,7 +197,11 @@ typedef struct {
     uint64_t* totals;      /* optional inout [4]: += accepted, rejected, failed, 0 */
     int64_t max_iters;     /* attempts per trajectory before DEGK_RC_MAXITERS; 0 => 1e7 for adaptive runs, no cap for fixed dt */
     int32_t engine;        /* degk_engine: which adaptive kernel generation to run */
-    int32_t reserved;
+    int32_t dae_init;      /* 1: before the first step, solve the algebraic equations of a mass-matrix DAE for consistent
+                              initial values of the algebraic states (reference gpu_initialization_solve,
+                              nlsolve/initialization.jl:1-54; trust-region Newton, tolerances 1e-6 for fixed dt, the
+                              solve's abstol / reltol when adaptive).  Trajectories whose initialisation fails are not
+                              integrated (DEGK_RC_INIT_FAILURE).  Not available with tstops / callbacks */
     const void* tstops;    /* kw `tstops`: n_tstops ascending times of the program's dtype (device pointer in
                               degk_solve, host pointer in degk_solve_host); needs a program built with
                               events != 0 */
@@ -211,6 +216,10 @@ typedef struct {
                               Per-problem `saveat` (reference kernels.jl:15-17, 89-91, src/solve.jl:226-250): every
                               trajectory brings its own grid of the SAME length n_saveat; `saveat` then points at
                               n_traj * saveat_stride values */
+    const int32_t* order;  /* optional (adaptive kernel): permutation of 0..n_traj-1; trajectories are STARTED in this
+                              order (e.g. sorted by a parameter that predicts the step count, so that the lanes of a
+                              warp finish together), results are written at each trajectory's own index.  Device
+                              pointer in degk_solve; ignored by degk_solve_host, the fixed-dt and the SDE kernels */
 } degk_solve_args;
 
 DEGK_API int degk_version(void);

@@ -213,3 +213,61 @@ def test_gpu_direct_mass_matrix_dae_bit_exact(oracle, alg):
         assert np.array_equal(g_ts, r["ts"]) and np.array_equal(g_us, r["us"], equal_nan=True), sorted(kw)
         assert (st["retcode"].cpu().numpy() == 1).all()
     assert np.abs(g_us[:, -1].sum(axis=1) - 1).max() < 0.01 and not np.isnan(g_us).any()
+
+
+# ------------------------------------------------------------------------------------------
+# DAE initialisation (reference kernels.jl:19-25, 93-99 -> nlsolve/initialization.jl; `ODEFunction(..., initialize=True)`)
+# ------------------------------------------------------------------------------------------
+def test_dae_init_restatement_solves_the_algebraic_rows():
+    from oracle.dae_init import dae_initialize
+    M = np.diag([1.0, 0.0])
+    f = lambda u, p, t: np.array([-u[0], u[1] * u[1] + u[0] - p[0]])
+    jac = lambda u, p, t: np.array([[-1.0, 0.0], [1.0, 2 * u[1]]])
+    u, ok = dae_initialize(f, jac, M, [1.0, 3.0], [2.0], 0.0, dtype=f64)
+    assert ok and u[0] == 1.0 and abs(u[1] - 1.0) < 1e-6
+    u, ok = dae_initialize(f, jac, M, [1.0, 3.0], [-5.0], 0.0, dtype=f64)     # u1^2 = -6: no consistent value
+    assert not ok
+    u, ok = dae_initialize(f, jac, np.eye(2), [1.0, 3.0], [2.0], 0.0)          # no algebraic rows: untouched
+    assert ok and np.array_equal(u, np.array([1.0, 3.0], f32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_gpu_dae_initialisation(adaptive):
+    import torch
+    import diffeqgpu_b200 as dg
+    from oracle.dae_init import dae_initialize
+    rhs = "    du[0] = -u[0];\n    du[1] = u[1] * u[1] + u[0] - p[0];\n"
+    jac = "    J[0][0] = (T)-1;\n    J[1][0] = (T)1;  J[1][1] = (T)2 * u[1];\n"
+    f = dg.ODEFunction(rhs=rhs, jac=jac, mass_matrix="    Mm[0][0] = (T)1;\n", n_state=2, n_param=1, initialize=True)
+    n = 257
+    ps = np.linspace(1.5, 6.0, n).astype(f32)[:, None]
+    ps[5, 0] = -5.0                                        # no consistent value: u1^2 = p - u0 < 0
+    prob = dg.ODEProblem(f, np.array([1.0, 3.0], f32), (0.0, 1.0), np.array([2.0], f32))
+    probs = dg.ProblemBatch.from_arrays(prob, p=ps, device="cuda:0")
+    sv = np.array([0.0, 0.5, 1.0], f32)
+    for alg in (dg.GPURosenbrock23(), dg.GPURodas5P()):
+        if adaptive:
+            ts, us, st = dg.vectorized_asolve(probs, prob, alg, dt=f32(0.01), saveat=sv, abstol=f32(1e-6), reltol=f32(1e-6), stats=True)
+        else:
+            ts, us, st = dg.vectorized_solve(probs, prob, alg, dt=f32(0.01), saveat=sv, stats=True)
+        torch.cuda.synchronize()
+        us, ts, rc = us.cpu().numpy(), ts.cpu().numpy(), st["retcode"].cpu().numpy()
+        ok = np.ones(n, bool); ok[5] = False
+        assert (rc[ok] == 1).all() and rc[5] == 7          # InitialFailure: not integrated, row 1 = prob.u0
+        assert np.array_equal(us[5, 0], np.array([1.0, 3.0], f32)) and ts[5, 0] == 0 and (ts[5, 1:] == 0).all()
+        fpy = lambda u, p, t: np.array([-u[0], u[1] * u[1] + u[0] - p[0]])
+        jpy = lambda u, p, t: np.array([[-1.0, 0.0], [1.0, 2 * u[1]]])
+        for i in (0, 17, 100, 256):
+            u_ref, ok_ref = dae_initialize(fpy, jpy, np.diag([1.0, 0.0]), [1.0, 3.0], ps[i], 0.0)
+            assert ok_ref and np.abs(us[i, 0] - u_ref).max() < 2e-6          # row 1 holds the initialised state
+        # the algebraic row holds along the whole solution: u1^2 + u0 = p, u0 = exp(-t)
+        res = us[ok, :, 1] ** 2 + us[ok, :, 0] - ps[ok]
+        assert np.abs(res).max() < 2e-4
+        assert np.abs(us[ok, -1, 0] - np.exp(-1.0)).max() < (2e-3 if not adaptive else 1e-3)
+    # without `initialize` the inconsistent u0 is integrated as given (row 1 = prob.u0)
+    f0 = dg.ODEFunction(rhs=rhs, jac=jac, mass_matrix="    Mm[0][0] = (T)1;\n", n_state=2, n_param=1)
+    prob0 = dg.ODEProblem(f0, np.array([1.0, 3.0], f32), (0.0, 1.0), np.array([2.0], f32))
+    ts, us = dg.vectorized_solve(dg.ProblemBatch.from_arrays(prob0, p=ps[:4], device="cuda:0"), prob0, dg.GPURosenbrock23(), dt=f32(0.01), saveat=sv)
+    torch.cuda.synchronize()
+    assert np.array_equal(us.cpu().numpy()[:, 0], np.tile(np.array([1.0, 3.0], f32), (4, 1)))

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include <cuda_runtime.h>
 #include "device/degk_common.cuh"
@@ -65,6 +66,8 @@ int main(int argc, char** argv) {
     const int reps = argc > 2 ? atoi(argv[2]) : 3;
     const int with_ts = argc > 3 ? atoi(argv[3]) : 1;
     const int with_stats = argc > 4 ? atoi(argv[4]) : 0;      // retcode / naccept / nreject arrays
+    const int sched = argc > 5 ? atoi(argv[5]) : 1;           // 0 static, 1 queue
+    const int sorted = argc > 6 ? atoi(argv[6]) : 0;          // 1: start order sorted by rho (p[1])
     constexpr int W = WSLOTS;
     typedef float T;
     const int nsv = 11;
@@ -87,9 +90,19 @@ int main(int argc, char** argv) {
     if (with_stats) { CK(cudaMalloc(&drc, (size_t)N * 4)); CK(cudaMalloc(&dna, (size_t)N * 4)); CK(cudaMalloc(&dnr, (size_t)N * 4)); }
     CK(cudaMalloc(&dtot, 32)); CK(cudaMalloc(&dctr, 8));
 
+    int* dorder = nullptr;
+    if (sorted) {
+        std::vector<int> ord((size_t)N);
+        for (long long i = 0; i < N; ++i) ord[i] = (int)i;
+        std::sort(ord.begin(), ord.end(), [&](int x, int y) { return hp[(size_t)x * 3 + 1] < hp[(size_t)y * 3 + 1]; });
+        CK(cudaMalloc(&dorder, (size_t)N * 4)); CK(cudaMemcpy(dorder, ord.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+    }
     KArgs k; memset(&k, 0, sizeof k);
     k.n_traj = N; k.u0 = du0; k.u0_stride = 0; k.p = dp; k.p_stride = 3; k.tspan = dtspan; k.tspan_stride = 0;
-    k.saveat = dsv; k.n_saveat = nsv; k.n_rows = nsv; k.us = dus; k.ts = dts; k.out_layout = LAYOUT_REF; k.schedule = SCHED_QUEUE;
+    k.saveat = dsv; k.n_saveat = nsv; k.n_rows = nsv; k.us = dus; k.ts = dts; k.out_layout = LAYOUT_REF; k.schedule = sched ? SCHED_QUEUE : SCHED_STATIC;
+#if GEN >= 4
+    k.order = dorder;
+#endif
     k.retcode = drc; k.naccept = dna; k.nreject = dnr; k.nsaved = dns;
     k.dt = 0.1f; k.abstol = 1e-6f; k.reltol = 1e-6f; k.totals = dtot; k.work_counter = dctr; k.max_iters = 10000000;
 
@@ -106,7 +119,7 @@ int main(int argc, char** argv) {
     const int per_thread = GEN >= 5 ? 2 * W : W;
     long long blocks = (N + DEGK_BLOCK2 * per_thread - 1) / (DEGK_BLOCK2 * per_thread);
     const long long resident = (long long)prop.multiProcessorCount * occ;
-    if (blocks > resident) blocks = resident;
+    if (sched && blocks > resident) blocks = resident;
 
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best = 1e30f;
@@ -142,10 +155,10 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < hrc.size(); ++i) cs += (unsigned long long)hrc[i] * (i % 1000003 + 1);
     }
     const double steps = (double)(tot[0] + tot[1]);
-    printf("{\"gen\": %d, \"strict\": %d, \"W\": %d, \"N\": %lld, \"regs\": %d, \"smem\": %zu, \"blocks_per_sm\": %d, \"ms\": %.3f, "
+    printf("{\"sched\": %d, \"sorted\": %d, \"gen\": %d, \"strict\": %d, \"W\": %d, \"N\": %lld, \"regs\": %d, \"smem\": %zu, \"blocks_per_sm\": %d, \"ms\": %.3f, "
            "\"gsteps_per_s\": %.2f, \"frac_of_74.45\": %.4f, \"acc\": %llu, \"rej\": %llu, \"fail\": %llu, "
            "\"sum_us\": \"%016llx\", \"sum_ts\": \"%016llx\", \"sum_nsaved\": \"%016llx\", \"sum_stats\": \"%016llx\"}\n",
-           GEN, (int)DEGK_STRICT, W, N, fa.numRegs, smem, occ, best, steps / best / 1e6, 263.0 * steps / (best * 1e-3) / 74.45e12,
+           sched, sorted, GEN, (int)DEGK_STRICT, W, N, fa.numRegs, smem, occ, best, steps / best / 1e6, 263.0 * steps / (best * 1e-3) / 74.45e12,
            tot[0], tot[1], tot[2], cu, ct, cn, cs);
     return 0;
 }
