@@ -66,17 +66,44 @@ DEGK_DEV void ode_solve_body(const KArgs& a, unsigned char* smem_raw) {
     }
     auto flush = [&]() {         // warp-cooperative: every lane of the warp calls it
         __syncwarp();
-        for (int j = 0; j < 32; ++j) {
-            const int n = __shfl_sync(0xffffffffu, nbuf, j);
-            if (n == 0) continue;
-            const i64 tr = __shfl_sync(0xffffffffu, traj, j);
-            const i64 kk = __shfl_sync(0xffffffffu, k0, j);
-            i64 nn = a.n_rows - kk;          // rows past len are dropped (the reference would write out of bounds)
-            nn = nn < 0 ? 0 : (nn < n ? nn : n);
-            const T* ub = wu + (size_t)j * ((size_t)N * R + 1);
-            T* ud = (T*)a.us + (tr * a.n_rows + kk) * N;
-            for (int w = (int)lane; w < (int)nn * N; w += 32) ud[w] = ub[w];
-            if (a.ts != nullptr && (i64)lane < nn) ((T*)a.ts)[tr * a.n_rows + kk + lane] = wt[(size_t)j * (R + 1) + lane];
+        // lock-step warp (the usual case: same tspan and dt for 32 consecutive trajectories): one flattened copy of
+        // the [32 trajectories][n rows][N] block -- lane-consecutive words, one index update per 32 words
+        const int n0 = __shfl_sync(0xffffffffu, nbuf, 0);
+        const i64 kk0 = __shfl_sync(0xffffffffu, k0, 0), tr0 = __shfl_sync(0xffffffffu, traj, 0);
+        if (__all_sync(0xffffffffu, nbuf == n0 && k0 == kk0 && traj == tr0 + (i64)lane) && n0 > 0 && kk0 + n0 <= a.n_rows) {
+            const int L = n0 * N, S = N * R + 1;
+            const size_t rs = (size_t)a.n_rows * N;
+            T* out = (T*)a.us + ((size_t)tr0 * a.n_rows + (size_t)kk0) * N;
+            int j = 0, w = (int)lane;
+            while (w >= L) { w -= L; ++j; }
+            for (int it = 0; it < L; ++it) {
+                out[(size_t)j * rs + w] = wu[j * S + w];
+                w += 32;
+                while (w >= L) { w -= L; ++j; }
+            }
+            if (a.ts != nullptr) {
+                T* tout = (T*)a.ts + (size_t)tr0 * a.n_rows + (size_t)kk0;
+                j = 0; w = (int)lane;
+                while (w >= n0) { w -= n0; ++j; }
+                for (int it = 0; it < n0; ++it) {
+                    tout[(size_t)j * a.n_rows + w] = wt[j * (R + 1) + w];
+                    w += 32;
+                    while (w >= n0) { w -= n0; ++j; }
+                }
+            }
+        } else {
+            for (int j = 0; j < 32; ++j) {
+                const int n = __shfl_sync(0xffffffffu, nbuf, j);
+                if (n == 0) continue;
+                const i64 tr = __shfl_sync(0xffffffffu, traj, j);
+                const i64 kk = __shfl_sync(0xffffffffu, k0, j);
+                i64 nn = a.n_rows - kk;          // rows past len are dropped (the reference would write out of bounds)
+                nn = nn < 0 ? 0 : (nn < n ? nn : n);
+                const T* ub = wu + (size_t)j * ((size_t)N * R + 1);
+                T* ud = (T*)a.us + (tr * a.n_rows + kk) * N;
+                for (int w = (int)lane; w < (int)nn * N; w += 32) ud[w] = ub[w];
+                if (a.ts != nullptr && (i64)lane < nn) ((T*)a.ts)[tr * a.n_rows + kk + lane] = wt[(size_t)j * (R + 1) + lane];
+            }
         }
         nbuf = 0;
         __syncwarp();
