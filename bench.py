@@ -195,6 +195,8 @@ def main():
     rank, local, world = init_from_env("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    from diffeqgpu_b200.parallel import bind_to_gpu_numa_node
+    bind_to_gpu_numa_node(local)          # pinned buffers and host threads next to the GPU (no-op on a single-node host)
     N = args.traj
     f32 = np.float32
     if args.config == "c5":

@@ -63,7 +63,7 @@ def summarize_rep(rep, name, workload):
         lines.append(f"#   {c:40s} n={n:5d}  inst={100 * e / tot_i:5.1f}%  samples={100 * s / tot_s:5.1f}%")
     lines.append("# opcodes of the every-iteration path: " + ", ".join(f"{k} {v}" for k, v in sorted(ops.items(), key=lambda x: -x[1])))
     (ROOT / "profiles" / f"{name}.txt").write_text("\n".join(lines) + "\n")
-    js = ROOT / "profiles" / "r1_ncu_summary.json"
+    js = ROOT / "profiles" / ("r2_ncu_summary.json" if name.startswith("r2") else "r1_ncu_summary.json")
     allj = json.loads(js.read_text()) if js.exists() else {}
     allj[name] = d
     js.write_text(json.dumps(allj, indent=1))
