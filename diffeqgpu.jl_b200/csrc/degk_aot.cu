@@ -18,8 +18,6 @@
 #include "device/degk_rosenbrock.cuh"
 #include "device/degk_kvaerno.cuh"
 #include "device/degk_ode_kernels.cuh"
-#include "device/degk_ode_kernels2.cuh"
-#include "device/degk_ode_kernels3.cuh"
 #include "device/degk_ode_kernels4.cuh"
 #include "device/degk_sde_kernels.cuh"
 #include "degk_internal.h"

@@ -223,7 +223,7 @@ struct Kvaerno {
             out[c] = fma_(w3, inner, fma_(theta, unew[c], th1 * uprev[c]));
         }
     }
-    // the deferred-save replay (degk_ode_kernels2.cuh) must rebuild the *adaptive* step's k1 / k2
+    // the deferred-save replay (degk_ode_saves.cuh) must rebuild the *adaptive* step's k1 / k2
     static constexpr bool REPLAY_ADAPTIVE = true;
 };
 

@@ -24,7 +24,7 @@
 //        - the service path tests "is a retire batch due" first and leaves in ~12 instructions otherwise;
 //        - save records of the packed build are replayed two per lane with the packed stepper.
 #pragma once
-#include "degk_ode_kernels3.cuh"
+#include "degk_ode_saves.cuh"
 #include "degk_dae_init.cuh"
 
 #ifndef DEGK4_HK
@@ -174,7 +174,10 @@ DEGK4_COLD void process_saves_packed(const KArgs& a, const SaveRec<float, Model:
 // ------------------------------------------------------------------------------------------
 // StepMath: the arithmetic that differs between the fp modes (error norm, PI controller).
 //   strict: gpu_tsit5_perform_step.jl:121-137 operation by operation (same as ode_asolve2_body / the oracle)
-//   fast:   L = log2(N * EEst^2), one exponent for accept and reject (see degk_ode_kernels3.cuh (4))
+//   fast:   log-domain PI controller.  With L = log2(N * EEst^2) (no mean, no square root) the accept and the reject
+//           branch share one exponent: fac = 2^clamp(-b1*L/2 + b2*lq'/2 + log2(gamma)), lq' = 0 on reject
+//           (dt / min(1/qmin, q11/gamma) = dt * max(qmin, fac); the upper clamp is inactive there) -- one MUFU.LG2 and
+//           one MUFU.EX2 replace the square root, two powers and three divisions
 // The controller memory `lq` holds qold (strict) or log2(N * qold^2) (fast).
 template <class T, int ORDER, int N, bool FAST> struct StepMath;
 

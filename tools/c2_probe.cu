@@ -19,8 +19,8 @@
 #include "device/degk_models.cuh"
 #include "device/gen_erk_tsit5.cuh"
 #include "device/degk_ode_kernels.cuh"
-#include "device/degk_ode_kernels2.cuh"
-#include "device/degk_ode_kernels3.cuh"
+#include "../../tools/experiments/degk_ode_kernels2_round1.cuh"
+#include "../../tools/experiments/degk_ode_kernels3_round1.cuh"
 #if GEN >= 4
 #include "device/degk_ode_kernels4.cuh"
 #endif

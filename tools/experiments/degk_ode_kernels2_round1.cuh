@@ -1,100 +1,9 @@
-// degk_ode_kernels2.cuh -- second-generation adaptive ensemble kernel.
-//
-// Replaces reference kernels.jl:74-152 (ode_asolve_kernel) like degk_ode_kernels.cuh does, with
-// changes that came out of the ncu profiles of the first kernel (profiles/):
-//
-//  (1) DEFERRED, BATCHED SAVES.  In the first kernel 25 % of all issued warp-instructions were
-//      the saveat block (dense-output polynomials + stores) executed with ~2 of 32 lanes active:
-//      with 32 independent adaptive trajectories per warp some lane crosses a save point in
-//      83 % of the iterations.  Here a lane that crosses a save point only appends a small
-//      record {trajectory, row, tprev, h, tnew, uprev} to a per-warp queue in shared memory.
-//      When 32 records are queued the whole warp processes them together, one record per lane:
-//      it re-evaluates the stages of that step (same inputs, same instruction sequence => same
-//      bits), interpolates and stores.  Re-computing a step costs less than 1 % of a trajectory
-//      (11 saves vs ~170 steps) and runs at full SIMT efficiency.
-//
-//  (2) PACKED PAIRS (W = 2, Float32 fast mode).  Each thread advances two trajectories held in
-//      the halves of 64-bit register pairs; stages, RHS and error estimate are FFMA2/FMUL2/FADD2
-//      (see degk_pack.cuh).  The kernel is issue-bound, so halving the instructions per
-//      trajectory nearly doubles the throughput of the arithmetic core.
-//
-//  (3) BRANCH-FREE STEP-SIZE CONTROL (fast mode).  The PI controller is evaluated in the log2
-//      domain: q = EEst^b1 / qold^b2 = 2^(b1*lE - b2*lq), so one MUFU.LG2 and one MUFU.EX2 replace
-//      the square root, two powers and three divisions; accept and reject values are both
-//      computed and selected, flags are bit masks, and only the rare events (save-point
-//      crossing, retirement, refill) branch.
-//
-// W = 1 gives the same kernel for Float64 and for the strict (bit-parity) fp mode.
+// Round-1 second-generation adaptive kernel body (strict build of round 1), kept for A/B runs with tools/c2_probe.cu.
+// Not part of libdegk: the library runs degk_ode_kernels4.cuh for both fp modes.
 #pragma once
-#include "degk_common.cuh"
-#include "degk_pack.cuh"
-
-#ifndef DEGK_RETIRE_BATCH
-#define DEGK_RETIRE_BATCH 6    // measured on C2 (8.4 M trajectories): 1: 90.0, 2: 94.2, 4: 97.7, 6: 98.5, 8: 98.4, 12: 97.2 G steps/s
-#endif
+#include "device/degk_ode_saves.cuh"
 
 namespace degk {
-
-// queue record of one deferred save (lives in shared memory)
-template <class T, int N>
-struct __align__(16) SaveRec {
-    int traj;           // index in this launch (n_traj < 2^31, checked by the host)
-    int cur;            // 1-based index of the first saveat entry to write
-    T tprev, h, tnew;
-    T u[N];             // state at the beginning of the step
-};
-
-template <class T, int N, int W>
-__host__ __device__ constexpr int asolve2_qcap() { return 32 + 32 * W; }
-
-// copy a record through 16-byte words so that the compiler emits vector shared-memory accesses
-template <class R>
-DEGK_DEV void rec_copy(R* dst, const R* src) {
-    static_assert(sizeof(R) % 16 == 0, "SaveRec must be a multiple of 16 bytes");
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    DEGK_UNROLL for (int i = 0; i < (int)(sizeof(R) / 16); ++i) d[i] = s[i];
-}
-
-// ------------------------------------------------------------------------------------------
-// steppers whose fixed-dt and adaptive attempts keep different interpolation data (Kvaerno) say so
-template <class...> struct replay_void_ { typedef void type; };
-template <class M, class = void> struct replay_adaptive_of { static constexpr bool value = false; };
-template <class M> struct replay_adaptive_of<M, typename replay_void_<decltype(M::REPLAY_ADAPTIVE)>::type> { static constexpr bool value = M::REPLAY_ADAPTIVE; };
-
-// One warp processes up to 32 queued save records, one per lane (scalar method).
-template <class T, class Model, class MethodS>
-DEGK_DEV void process_saves(const KArgs& a, const SaveRec<T, Model::N>* q, int first, int count,
-                            const T* sv) {
-    constexpr int N = Model::N;
-    const int lane = (int)lane_id();
-    if (lane < count) {
-        SaveRec<T, N> r;
-        rec_copy(&r, q + first + lane);
-        T uprev[N], unew[N], err[N];
-        T p[Model::NP > 0 ? Model::NP : 1];
-        DEGK_UNROLL for (int c = 0; c < N; ++c) uprev[c] = r.u[c];
-        if (Model::NP > 0) {
-            const T* pp = (const T*)a.p + (i64)r.traj * a.p_stride;
-            DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) p[c] = pp[c];
-        }
-        const T tprev = r.tprev, h = r.h, tnew = r.tnew;
-        typename MethodS::Keep K;
-        MethodS::init(K, uprev, p, tprev);                  // FSAL k1 = f(uprev, p, tprev)
-        MethodS::template attempt<replay_adaptive_of<MethodS>::value>(K, uprev, p, tprev, h, unew, err);
-        MethodS::on_accept(K);
-        int cur = r.cur;
-        while (cur <= a.n_saveat && sv[cur - 1] <= tnew) {  // integrator_utils.jl:34-47
-            const T savet = sv[cur - 1];
-            const T theta = (savet - tprev) / h;
-            T v[N];
-            MethodS::interp(K, theta, h, uprev, unew, p, tprev, v);
-            store_u<T, N>(a, r.traj, cur - 1, v);
-            store_t<T>(a, r.traj, cur - 1, savet);
-            ++cur;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 template <class T, class Model, template <class, class> class MethodT, int W>

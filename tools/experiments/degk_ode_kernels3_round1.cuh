@@ -1,80 +1,9 @@
-// degk_ode_kernels3.cuh -- third-generation adaptive ensemble kernel (fast fp mode).
-//
-// Same job as ode_asolve2_body (reference kernels.jl:74-152 + the adaptive step! of each
-// solver) and the same building blocks (persistent warps, per-warp problem pool, deferred
-// batched saves, packed pairs).  What changed came out of the ncu profile of the second
-// generation (profiles/r1_c2_v2_fast.txt): 523 warp-instructions per loop iteration of which
-// only 155 were stage/RHS arithmetic, issue slots 69 % busy, ALU pipe 47 %, FMA pipe 50 %.
-// The non-arithmetic part is rebuilt so that the common iteration has no divergent code at all:
-//
-//  (1) BRANCH-FREE PUSH.  With 64 trajectories per warp some lane crosses a save point in
-//      ~99 % of the iterations, so the `if (crossing) { build record; advance cursor }` block
-//      (~55 instructions per slot, executed with 2-3 active lanes) ran almost every time.  Here
-//      the record goes out through predicated 16-byte shared-memory stores at a position
-//      computed from one ballot per slot, and the save cursor advances with selects.
-//      Several save points inside one step (rare) are detected with one compare and handled in
-//      the service path.
-//  (2) LIVE = (h >= dtmin).  A slot that stopped carries h = -1, so `dt < dtmin` (the
-//      reference's error check, gpu_tsit5_perform_step.jl:102) doubles as the liveness test and
-//      the have/done/fail masks leave the loop.  Return codes are derived when the slot retires:
-//      t >= tf -> Success; attempts >= maxiters -> MaxIters; 0 <= h < dtmin -> DtLessThanMin.
-//  (3) SERVICE PATH.  Retire, refill and termination tests run only in the iteration after
-//      some slot stopped (one vote per iteration instead of two ballots + popcounts).
-//  (4) PACKED CONTROLLER.  Error norm, log-domain PI controller and the time bookkeeping of
-//      both slots use FFMA2/FMUL2/FADD2; the accept and reject branches of the controller
-//      share one exponent: fac = 2^clamp(-b1*lE + b2*lq' + log2(gamma)), lq' = 0 on reject
-//      (dt/min(1/qmin, q11/gamma) = dt*max(qmin, fac); the upper clamp is inactive there).
-//      The norm is kept as L = log2(N*EEst^2), which removes the mean and the 1/2.
-//
-// Used for DEGK_STRICT == 0 only: the strict build keeps ode_asolve2_body, whose control flow
-// mirrors the oracle statement by statement.
+// Round-1 third-generation adaptive kernel body (fast build of round 1: 125.8 G steps/s on C2), kept for A/B runs with
+// tools/c2_probe.cu.  Not part of libdegk: the library runs degk_ode_kernels4.cuh for both fp modes.
 #pragma once
-#include "degk_ode_kernels2.cuh"
+#include "device/degk_ode_saves.cuh"
 
 namespace degk {
-
-// ---- per-half helpers (scalar overloads serve W == 1) ----
-DEGK_DEV float  vmaxabs(float a, float b)   { return fmaxf(fabsf(a), fabsf(b)); }
-DEGK_DEV double vmaxabs(double a, double b) { return fmax(fabs(a), fabs(b)); }
-DEGK_DEV Pk2 vmaxabs(Pk2 a, Pk2 b) { return Pk2(vmaxabs(a.lo(), b.lo()), vmaxabs(a.hi(), b.hi())); }
-DEGK_DEV float  vrcp(float x)  { return rcp_(x); }
-DEGK_DEV double vrcp(double x) { return 1.0 / x; }
-DEGK_DEV Pk2 vrcp(Pk2 x) { return Pk2(rcp_(x.lo()), rcp_(x.hi())); }
-DEGK_DEV float  vlog2(float x)  { return log2_(x); }
-DEGK_DEV double vlog2(double x) { return log2(x); }
-DEGK_DEV Pk2 vlog2(Pk2 x) { return Pk2(log2_(x.lo()), log2_(x.hi())); }
-DEGK_DEV float  vexp2(float x)  { return exp2_(x); }
-DEGK_DEV double vexp2(double x) { return exp2(x); }
-DEGK_DEV Pk2 vexp2(Pk2 x) { return Pk2(exp2_(x.lo()), exp2_(x.hi())); }
-DEGK_DEV float  vclamp(float x, float lo, float hi)    { return fminf(fmaxf(x, lo), hi); }   // NaN -> lo
-DEGK_DEV double vclamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
-DEGK_DEV Pk2 vclamp(Pk2 x, float lo, float hi) { return Pk2(vclamp(x.lo(), lo, hi), vclamp(x.hi(), lo, hi)); }
-
-// predicated 16-byte shared-memory store: no branch, inactive lanes store nothing
-DEGK_DEV void sts128_if(bool pred, u32 saddr, uint4 w) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.v4.u32 [%1], {%2, %3, %4, %5};\n\t}"
-                 :: "r"((u32)pred), "r"(saddr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-}
-// keep an address in a register: stops the compiler from re-deriving it from %tid / the shared
-// window base in every loop iteration (it did: 2 x S2R + 8 integer instructions per iteration)
-DEGK_DEV u32 opaque(u32 x) { asm volatile("" : "+r"(x)); return x; }
-DEGK_DEV float  lds_(u32 saddr, float)  { float v;  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr)); return v; }
-DEGK_DEV double lds_(u32 saddr, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr)); return v; }
-
-// in-place predicated increment `if (pred) ++x` as ONE predicated instruction (see assign_if)
-DEGK_DEV void inc_if(bool pred, u32& x) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(x) : "r"((u32)pred));
-}
-DEGK_DEV void inc_if(bool pred, int& x) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(x) : "r"((u32)pred));
-}
-
-template <class R>
-DEGK_DEV void rec_store_if(bool pred, u32 saddr, const R& r) {
-    static_assert(sizeof(R) % 16 == 0, "SaveRec must be a multiple of 16 bytes");
-    const uint4* s = reinterpret_cast<const uint4*>(&r);
-    DEGK_UNROLL for (int i = 0; i < (int)(sizeof(R) / 16); ++i) sts128_if(pred, saddr + 16u * i, s[i]);
-}
 
 // ------------------------------------------------------------------------------------------
 template <class T, class Model, template <class, class> class MethodT, int W>
@@ -454,17 +383,6 @@ DEGK_DEV void ode_asolve3_body(const KArgs& a, unsigned char* smem_raw) {
         __syncwarp();
     }
     add_totals<T>(a, tot_acc, tot_rej, tot_fail);
-}
-
-// the adaptive kernel body of this build: generation 2 mirrors the oracle statement by statement
-// (strict fp mode), generation 3 is the fast-mode kernel
-template <class T, class Model, template <class, class> class MethodT, int W>
-DEGK_DEV void ode_asolve_gen_body(const KArgs& a, unsigned char* smem_raw) {
-#if DEGK_STRICT || defined(DEGK_FAST_GEN2)
-    ode_asolve2_body<T, Model, MethodT, W>(a, smem_raw);
-#else
-    ode_asolve3_body<T, Model, MethodT, W>(a, smem_raw);
-#endif
 }
 
 }  // namespace degk

@@ -151,7 +151,7 @@ struct Asolve5 {
                 donem |= (u32)(!hv & (S.traj[s] >= 0)) << s;
             }
             // several save points inside one accepted step: the queued record covers all of them (the replay
-            // loops), skip the cursor past them (see degk_ode_kernels3.cuh for why `next_save <= t` identifies them)
+            // loops), skip the cursor past them (see degk_ode_kernels4.cuh for why `next_save <= t` identifies them)
             DEGK_UNROLL for (int s = 0; s < W; ++s) {
                 if (S.next_save[s] <= S.t[s] && S.nacc[s] != 0u) {
                     while (S.cur[s] <= c.nsv && save_time(c, S.cur[s]) <= S.t[s]) ++S.cur[s];
@@ -441,7 +441,7 @@ struct Asolve5 {
         c.kInf = (T)__longlong_as_double(0x7ff0000000000000LL);   // +inf: "no further save point"
         c.dtmin = MethodS::dtmin();
         c.kDead = (T)-1;                     // h of a slot that is not integrating
-        // fast controller constants in the L = log2(N * EEst^2) representation (degk_ode_kernels3.cuh (4))
+        // fast controller constants in the L = log2(N * EEst^2) representation (degk_ode_kernels4.cuh, StepMath)
         const double lgN = log2((double)N), lgGamma = log2(9.0 / 10.0);
         c.b1h = (T)(0.5 * 7.0 / (10.0 * MethodS::ORDER));
         c.b2h = (T)(0.5 * 2.0 / (5.0 * MethodS::ORDER));
