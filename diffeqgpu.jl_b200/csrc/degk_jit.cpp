@@ -182,6 +182,13 @@ static int save_rec_bytes(int dtype, int n_state) {
     return (b + 15) / 16 * 16;           // __align__(16)
 }
 
+// host-side mirror of degk::asolve4_qcap<T, N, W>() (checked by a static_assert in the JIT source): 32 lanes x
+// save_queue_depth records, plus the records' worth of bytes that hold the flush directory
+static int save_queue_cap(int rec_bytes, int slots) {
+    const int depth = rec_bytes <= 32 ? 4 * slots : (rec_bytes <= 64 ? 2 * slots : slots + 2);
+    return 32 * depth + (64 * depth + rec_bytes - 1) / rec_bytes;
+}
+
 // `slots` = trajectories per thread of the second-generation adaptive kernel (1 or 2)
 static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::string& src) {
     const bool is_sde = d->alg == DEGK_ALG_EM || d->alg == DEGK_ALG_SIEA;
@@ -366,12 +373,14 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                // per-problem saveat grids and grids too long for shared memory
                "extern \"C\" __global__ void __launch_bounds__(DEGK_JIT_BLOCK) degk_jit_adaptive(const degk::KArgs a) {\n"
                "    degk::ode_asolve_body<REAL, MODEL, METHOD>(a);\n}\n";
+        const int rec_bytes = save_rec_bytes(d->dtype, d->rhs_src ? d->n_state : builtin_n_state(d->builtin));
         snprintf(buf, sizeof buf,
                  "static_assert(sizeof(degk::SaveRec<REAL, MODEL::N>) == %d, \"host/device SaveRec size mismatch\");\n"
+                 "static_assert(degk::asolve4_qcap<REAL, MODEL::N, %d>() == %d, \"host/device save-queue capacity mismatch\");\n"
                  "extern \"C\" __global__ void __launch_bounds__(%d, (degk::asolve4_minblocks<REAL, METHOD>())) degk_jit_adaptive2(const degk::KArgs a) {\n"
                  "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
                  "    degk::ode_asolve4_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
-                 save_rec_bytes(d->dtype, d->rhs_src ? d->n_state : builtin_n_state(d->builtin)), DEGK_BLOCK2, slots);
+                 rec_bytes, slots, save_queue_cap(rec_bytes, slots), DEGK_BLOCK2, slots);
         src += buf;
     }
     return DEGK_OK;
@@ -496,8 +505,8 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
     prog->info.max_blocks_per_sm = v;
     if (f2) {
         prog->w2 = slots;
-        prog->qcap2 = (d->fp_mode != DEGK_FP_STRICT && slots == 2 && d->dtype != DEGK_F64) ? 128 : 32 + 32 * slots;   // asolve4_qcap
         prog->rec_bytes2 = save_rec_bytes(d->dtype, prog->info.n_state);
+        prog->qcap2 = save_queue_cap(prog->rec_bytes2, slots);
         DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, f2)); prog->info.regs_adaptive2 = v;
         DRV(ctx, g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f2)); prog->info.local_bytes_adaptive2 = v;
         prog->info.slots_per_thread2 = slots;

@@ -10,28 +10,28 @@
 //      only in StepMath<> below.  The strict instantiation is compared bit for bit with the CPU oracle
 //      (tests/test_gpu_parity.py), which pins the queue / push / multi-crossing / retire logic of the kernel
 //      that produces the headline number.
-//  (2) The cost model changed.  tools/pipe_probe.cu (profiles/r2_pipe_probe*.jsonl) shows that on sm_100 an
-//      SM sub-partition spends ~1 cycle per issued instruction plus a second cycle per packed FP32
-//      instruction, and a THIRD cycle when a packed instruction reads three register pairs (6 registers;
-//      the register file feeds two pairs per 2 cycles).  So: (a) stage sums use the h-scaled form of the
-//      generated steppers (attempt_hk: immediates + two register pairs), (b) everything that is not stage
-//      arithmetic is counted in instructions, not in "ALU cycles":
-//        - attempt counters are implicit (pass number at start / stop), the max-iteration test is one
-//          compare per thread, the service path finalises them;
+//  (2) The cost model changed.  tools/pipe_probe.cu (profiles/r2_pipe_probe*.jsonl) shows that on sm_100 the
+//      costs of the instructions of one warp ADD UP at the dispatch port: ~2.08 cycles per packed FP32
+//      instruction with two register-pair operands (3.06 with three), ~0.8-1.1 per two-source ALU instruction,
+//      ~2 per three-source integer instruction, ~4 per POPC -- nothing hides "in the shadow" of the FMA pipe.
+//      So: (a) stage sums use the h-scaled form of the generated steppers (attempt_hk: immediates + two
+//      register pairs), (b) everything that is not stage arithmetic is counted in instructions:
+//        - the save queue is lane-private (degk_ode_saves.cuh): a push is two predicated stores, two predicated
+//          adds and one predicated load of the next save time; ranks, compaction and the cursor fix-up after a
+//          step across several save points live in the service path;
+//        - the fast build derives the landing on tf from the exact remainder tf - (t + h) and lets a finished
+//          slot die by itself (its next step is < dtmin): no stop / park selects in the loop;
+//        - the maximum-iteration test only raises the service flag, the service path parks the slot;
 //        - trajectory start-up work that does not depend on the integration (row 0, the t0 pre-fill of ts,
 //          empty or invalid time spans) is done by the full warp when it loads 32 problems into its pool;
 //          retiring a slot is a handful of scattered 4-byte stores;
-//        - the service path tests "is a retire batch due" first and leaves in ~12 instructions otherwise;
-//        - save records of the packed build are replayed two per lane with the packed stepper.
+//        - the service path tests "is a retire batch due" first and leaves in ~12 instructions otherwise.
 #pragma once
 #include "degk_ode_saves.cuh"
 #include "degk_dae_init.cuh"
 
 #ifndef DEGK4_HK
 #define DEGK4_HK 1          // h-scaled stage sums in the fast build
-#endif
-#ifndef DEGK4_PREPLAY
-#define DEGK4_PREPLAY 0     // packed replay of deferred saves in the packed build (measured: +0.3 % on C2, 128 registers)
 #endif
 #ifndef DEGK4_SERVICE_PERIOD
 #define DEGK4_SERVICE_PERIOD 8   // passes between two looks at the stopped slots (power of two)
@@ -77,8 +77,10 @@ template <class T> struct Slots4<T, 2, false> {
 };
 template <class T, int W> __host__ __device__ constexpr bool slots4_packed() { return !DEGK_STRICT && W == 2 && sizeof(T) == 4; }
 
+// save-queue capacity per warp in records: 32 lanes x depth, plus the records' worth of bytes that hold the
+// flush directory (one u16 per record)
 template <class T, int N, int W> __host__ __device__ constexpr int asolve4_qcap() {
-    return (!DEGK_STRICT && DEGK4_PREPLAY && W == 2 && sizeof(T) == 4) ? 128 : 32 + 32 * W;      // packed replay drains 64 records at a time
+    return 32 * save_queue_depth<T, N, W>() + (int)((64 * save_queue_depth<T, N, W>() + sizeof(SaveRec<T, N>) - 1) / sizeof(SaveRec<T, N>));
 }
 template <class T, int N, int NP> __host__ __device__ constexpr int asolve4_pool_words() { return N + NP + 3; }   // u0, p, t0, tf, first cursor
 template <class T, int N, int NP, int W>
@@ -91,13 +93,14 @@ template <class M, class = void> struct has_hk_of { static constexpr bool value 
 template <class M> struct has_hk_of<M, typename replay_void_<decltype(M::HAS_HK)>::type> { static constexpr bool value = M::HAS_HK; };
 
 // resident blocks (of DEGK_BLOCK2 = 128 threads) per SM the kernel is compiled for.  Measured on C2 (Lorenz,
-// GPUTsit5, 8.4 M trajectories; tools/c2_probe.cu): packed fast build 3: 121, 4: 128, 5 (96 registers, no spills):
-// 133, 6 (80 registers, 100 B spilled): 128 G steps/s; one-slot strict build 4: 38.0, 6: 41.4, 8: 41.0.
+// GPUTsit5, 8.4 M trajectories; tools/c2_probe.cu, profiles/r2_c2_lanequeue.md): packed fast build 4 (127 registers,
+// no spills): 134.8, 5 (96 registers, ~100 B of loop-carried state in local memory): 131.5 G steps/s; one-slot
+// strict build 4: 38.2, 5: 40.3, 6 (80 registers): 41.4 (47.8 with the shared controller logarithm).
 // Steppers with more live stage vectors (Vern7/9, the Rosenbrock family) keep the 128-register budget.
 template <class T, class MS> __host__ __device__ constexpr int asolve4_minblocks() {
     if (sizeof(T) != 4) return 1;
     if (!MS::ALWAYS_SOLVED) return 4;
-    if (has_hk_of<MS>::value) return DEGK_STRICT ? 6 : 5;        // FSAL, <= 7 stages
+    if (has_hk_of<MS>::value) return DEGK_STRICT ? 6 : 4;        // FSAL, <= 7 stages
     return 4;
 }
 
@@ -111,95 +114,58 @@ DEGK_DEV bool attempt4(KeepT& K, const V (&u)[N], const V* p, V t, V h, V (&unew
 }
 
 // ------------------------------------------------------------------------------------------
-// packed replay of deferred saves (fast build, W = 2): lane l handles records first + 2l and first + 2l + 1
-#ifndef DEGK4_REPLAY_INLINE
-#define DEGK4_REPLAY_INLINE 0
-#endif
-#if DEGK4_REPLAY_INLINE
-#define DEGK4_COLD DEGK_DEV
-#else
-#define DEGK4_COLD __device__ __noinline__      // keeps the replay's registers out of the loop's allocation
-#endif
-template <class Model, class MethodV>
-DEGK4_COLD void process_saves_packed(const KArgs& a, const SaveRec<float, Model::N>* q, int first, int count, u32 sv_saddr) {
-    constexpr int N = Model::N;
-    constexpr int NPA = Model::NP > 0 ? Model::NP : 1;
-    constexpr bool HK = use_hk<MethodV>();
-    const int lane = (int)lane_id();
-    const int i0 = 2 * lane, i1 = 2 * lane + 1;
-    if (i0 < count) {
-        const bool two = i1 < count;
-        SaveRec<float, N> r0, r1;
-        rec_copy(&r0, q + first + i0);
-        rec_copy(&r1, q + first + (two ? i1 : i0));
-        Pk2 uprev[N], unew[N], err[N], p[NPA];
-        DEGK_UNROLL for (int c = 0; c < N; ++c) uprev[c] = Pk2(r0.u[c], r1.u[c]);
-        if (Model::NP > 0) {
-            const float* p0 = (const float*)a.p + (i64)r0.traj * a.p_stride;
-            const float* p1 = (const float*)a.p + (i64)r1.traj * a.p_stride;
-            DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) p[c] = Pk2(p0[c], p1[c]);
-        }
-        const Pk2 tprev(r0.tprev, r1.tprev), h(r0.h, r1.h);
-        typename MethodV::Keep K;
-        MethodV::init(K, uprev, p, tprev);
-        attempt4<HK, MethodV>(K, uprev, p, tprev, h, unew, err);
-        MethodV::on_accept(K);
-        int cur0 = r0.cur, cur1 = r1.cur;
-        for (;;) {                                               // integrator_utils.jl:34-47, both halves in lock step
-            const float s0 = lds_(sv_saddr + (u32)cur0 * 4u, 0.f), s1 = lds_(sv_saddr + (u32)cur1 * 4u, 0.f);
-            const bool m0 = s0 <= r0.tnew, m1 = two && s1 <= r1.tnew;
-            if (!(m0 | m1)) break;
-            const Pk2 theta((s0 - r0.tprev) / r0.h, (s1 - r1.tprev) / r1.h);
-            Pk2 v[N];
-            if constexpr (HK) MethodV::interp_hk(K, theta, h, uprev, unew, p, tprev, v);
-            else MethodV::interp(K, theta, h, uprev, unew, p, tprev, v);
-            if (m0) {
-                float o[N];
-                DEGK_UNROLL for (int c = 0; c < N; ++c) o[c] = v[c].lo();
-                store_u<float, N>(a, r0.traj, cur0 - 1, o);
-                store_t<float>(a, r0.traj, cur0 - 1, s0);
-                ++cur0;
-            }
-            if (m1) {
-                float o[N];
-                DEGK_UNROLL for (int c = 0; c < N; ++c) o[c] = v[c].hi();
-                store_u<float, N>(a, r1.traj, cur1 - 1, o);
-                store_t<float>(a, r1.traj, cur1 - 1, s1);
-                ++cur1;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // StepMath: the arithmetic that differs between the fp modes (error norm, PI controller).
 //   strict: gpu_tsit5_perform_step.jl:121-137 operation by operation (same as ode_asolve2_body / the oracle)
 //   fast:   log-domain PI controller.  With L = log2(N * EEst^2) (no mean, no square root) the accept and the reject
 //           branch share one exponent: fac = 2^clamp(-b1*L/2 + b2*lq'/2 + log2(gamma)), lq' = 0 on reject
 //           (dt / min(1/qmin, q11/gamma) = dt * max(qmin, fac); the upper clamp is inactive there) -- one MUFU.LG2 and
 //           one MUFU.EX2 replace the square root, two powers and three divisions
-// The controller memory `lq` holds qold (strict) or log2(N * qold^2) (fast).
+// The controller memory `lq` holds qold^beta2 (strict) or log2(N * qold^2) (fast).
 template <class T, int ORDER, int N, bool FAST> struct StepMath;
+
+// EEst^beta1 and max(EEst, qoldinit)^beta2 for the strict controller.  Float32: Julia's `^` is
+// Float32(exp2(log2(Float64 x) * Float64 y)) (degk_common.cuh pow_), so the two powers of one base share the
+// Float64 logarithm -- the same double feeds both exp2, bit for bit what two separate pow_ calls return, for one
+// FP64 log2 less per attempt (the controller memory holds qold^beta2 instead of qold for that reason).
+template <int ORDER, class T>
+DEGK_DEV void ctl_powers(T EEst, T lq0, T& q11, T& lq_acc) {
+    typedef Ctl<T, ORDER> C;
+    q11 = pow_(EEst, C::beta1());
+    lq_acc = EEst < C::qoldinit() ? lq0 : pow_(EEst, C::beta2());       // NaN propagates like jl_max
+}
+#if DEGK_STRICT
+template <int ORDER>
+DEGK_DEV void ctl_powers(float EEst, float lq0, float& q11, float& lq_acc) {
+    typedef Ctl<float, ORDER> C;
+    const double lg = log2((double)EEst);
+    const float p1 = (float)exp2(lg * (double)C::beta1()), p2 = (float)exp2(lg * (double)C::beta2());
+    q11 = EEst == 1.0f ? 1.0f : p1;
+    lq_acc = EEst < C::qoldinit() ? lq0 : (EEst == 1.0f ? 1.0f : p2);
+}
+#endif
 
 template <class T, int ORDER, int N>
 struct StepMath<T, ORDER, N, false> {
     typedef Ctl<T, ORDER> C;
-    static DEGK_DEV T lq_init() { return C::qoldinit(); }
+    static DEGK_DEV T lq_init() { return pow_(C::qoldinit(), C::beta2()); }
     // per slot: sum of squares of tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol)
     static DEGK_DEV T scaled_sq(T uo, T un, T e, T abstol, T reltol) {
         const T sc = abstol + jl_max(abs_(uo), abs_(un)) * reltol;
         const T v = e / sc;
         return v * v;
     }
+    // lq = qold^beta2, lq0 = qoldinit^beta2
     // -> reject?, candidate step (before the tf clamp), controller memory after an accepted step
-    static DEGK_DEV void control(T accn, T lq, T h, bool& reject, T& hf, T& lq_acc) {
+    static DEGK_DEV void control(T accn, T lq, T lq0, T h, bool& reject, T& hf, T& lq_acc) {
         const T EEst = sqrt_(mean_<T, N>(accn));
-        T q, q11 = (T)0;
+        T q11;
+        ctl_powers<ORDER>(EEst, lq0, q11, lq_acc);       // lq_acc = max(EEst, qoldinit)^beta2
+        T q;
         if (EEst == (T)0) {
             q = (T)1 / C::qmax();
+            q11 = (T)0;
         } else {
-            q11 = pow_(EEst, C::beta1());
-            q = q11 / pow_(lq, C::beta2());
+            q = q11 / lq;
         }
         reject = EEst > (T)1;
         if (reject) {
@@ -208,7 +174,6 @@ struct StepMath<T, ORDER, N, false> {
             q = jl_max((T)1 / C::qmax(), jl_min((T)1 / C::qmin(), q / C::gamma()));
             hf = h / q;
         }
-        lq_acc = jl_max(EEst, C::qoldinit());
     }
     static DEGK_DEV T next_h_accept(T hf, T rem) { return jl_min(abs_(hf), abs_(rem)); }
 };
@@ -226,16 +191,23 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
     constexpr int N = Model::N;
     constexpr int NPA = Model::NP > 0 ? Model::NP : 1;
     constexpr int QCAP = asolve4_qcap<T, N, W>();
-    constexpr bool PREPLAY = PACKED && DEGK4_PREPLAY;            // deferred saves replayed two per lane with the packed stepper
-    constexpr int QBATCH = PREPLAY ? 64 : 32;                    // records drained at a time
+    constexpr int QDEPTH = save_queue_depth<T, N, W>();             // records per lane of the lane-private save queue
+    static_assert(QDEPTH > W, "a lane must be able to queue one record per slot and pass");
     constexpr bool HK = use_hk<MethodV>();
+    // fast build: a slot that lands on tf gets a next step < dtmin from the exact remainder and so stops by itself;
+    // the strict build follows the reference's formulas, where the slot has to be parked explicitly
+    constexpr bool PARK_NATURAL = FAST;
     typedef SaveRec<T, N> Rec;
+    constexpr int QBATCH = 32;                                   // records replayed at a time, one per lane
+    constexpr u32 QSTRIDE = 32u * (u32)sizeof(Rec);              // bytes between two records of one lane
 
-    const T abstol = (T)a.abstol, reltol = (T)a.reltol;
+    // tolerances in the working precision, pinned in registers (left to itself the compiler re-converts the
+    // Float64 kernel arguments in every pass: two quarter-rate F2F per pass)
+    const T abstol = opaque_f((T)a.abstol), reltol = opaque_f((T)a.reltol);
     const bool has_saveat = a.saveat != nullptr;
     const int nsv = (int)opaque((u32)(has_saveat ? a.n_saveat : 0));
     const u32 lane = lane_id();
-    const u32 lt_mask = (1u << lane) - 1u;
+    const u32 lt_mask = (1u << lane) - 1u;                    // (service path only)
     const int warp_in_block = (int)(threadIdx.x >> 5);
     const int nwarps = (int)(blockDim.x >> 5);
     const u32 max_it = a.max_iters > 0x3fffffffLL ? 0x3fffffffu : (u32)a.max_iters;
@@ -255,8 +227,14 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
 
     // shared memory: [per-warp save queues][per-warp problem pools][saveat copy + 2 x inf]
     constexpr int PW = asolve4_pool_words<T, N, Model::NP>();    // u0, p, t0, tf, first save cursor (0: nothing to integrate)
+    // save queue of this warp: record k of lane l at index l + 32 k; behind the 32 * QDEPTH records the flush directory
     Rec* queue = (Rec*)smem_raw + (size_t)warp_in_block * QCAP;
-    const u32 queue_saddr = opaque((u32)__cvta_generic_to_shared(queue));
+    unsigned short* qdir = (unsigned short*)(queue + 32 * QDEPTH);
+    const u32 queue_saddr = (u32)__cvta_generic_to_shared(queue);
+    const u32 q0 = queue_saddr + lane * (u32)sizeof(Rec);                   // this lane's first record
+    // qaddr >= qtrig: fewer than W free records (pinned in a register: the compiler would re-derive it from %tid in every pass)
+    const u32 qtrig = opaque(queue_saddr + (u32)(QDEPTH - W + 1) * QSTRIDE);
+    u32 qaddr = opaque(q0);                  // this lane's next free record
     T* pool = (T*)(smem_raw + (size_t)nwarps * QCAP * sizeof(Rec)) + (size_t)warp_in_block * 32 * PW;
     T* sv_s = (T*)(smem_raw + (size_t)nwarps * QCAP * sizeof(Rec)) + (size_t)nwarps * 32 * PW;
     // saveat is staged in shared memory as a 1-based array with two +inf sentinels behind the last entry (the host
@@ -266,18 +244,19 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
     __syncthreads();
     const u32 sv_saddr = opaque((u32)__cvta_generic_to_shared(sv_s) - (u32)sizeof(T));   // 1-based
     auto save_time = [&](int c) -> T { return lds_(sv_saddr + (u32)c * (u32)sizeof(T), (T)0); };   // c <= nsv + 2
-    int qcount = 0;                          // warp-uniform
+    auto cursor_of = [&](u32 addr) -> int { return (int)((addr - sv_saddr) / (u32)sizeof(T)); };
 
     // per-thread state: W trajectories ("slots")
     V u[N], unew[N], err[N], p[NPA];
     typename MethodV::Keep K;
-    T t[W], h[W], tf[W], next_save[W], next_save2[W], lq[W];
-    int cur[W], traj[W];
+    T t[W], h[W], tf[W], next_save[W], lq[W];
+    u32 ca[W];                               // save cursor as the shared-memory address of its saveat entry
+    int traj[W];
     u32 natt[W], nacc[W];
     u32 singm = 0;                           // bit s: W was singular
     DEGK_UNROLL for (int s = 0; s < W; ++s) {
-        traj[s] = -1; cur[s] = 1; natt[s] = 0; nacc[s] = 0;
-        t[s] = (T)0; h[s] = kDead; tf[s] = (T)0; next_save[s] = kInf; next_save2[s] = kInf; lq[s] = lqInit;
+        traj[s] = -1; ca[s] = sv_saddr + (u32)sizeof(T); natt[s] = 0; nacc[s] = 0;
+        t[s] = (T)0; h[s] = kDead; tf[s] = (T)0; next_save[s] = kInf; lq[s] = lqInit;
     }
     DEGK_UNROLL for (int c = 0; c < N; ++c) { u[c] = V((T)0); unew[c] = V((T)0); err[c] = V((T)0); }
     DEGK_UNROLL for (int c = 0; c < NPA; ++c) p[c] = V((T)0);
@@ -356,9 +335,8 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
         t[s] = t0_; tf[s] = tf_;
         lq[s] = lqInit;
         natt[s] = 0; nacc[s] = 0;
-        cur[s] = c1;
+        ca[s] = sv_saddr + (u32)c1 * (u32)sizeof(T);
         next_save[s] = save_time(c1);
-        next_save2[s] = save_time(c1 + 1);
         traj[s] = a.order ? a.order[pool_base + ei] : pool_base + ei;
         const T h0 = (T)a.dt;
         // dt0 < dtmin errors at the first attempt; non-finite time data cannot be integrated:
@@ -368,13 +346,53 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
         if (h[s] >= dtmin) freshm |= (1u << s);
     };
 
-    bool service = true;                     // warp-uniform: a slot stopped (or start of the kernel)
+    // Flush the lane-private save queue (warp-collective).  Full batches of 32 records are processed one per lane;
+    // the < 32 left-over records are re-homed one per lane (which also levels the per-lane counts), unless `final`.
+    // (A packed replay -- two records per lane through the packed stepper -- halves the issue cost per record but
+    //  was measured slower: inlined it pushes loop-carried state of the attempt loop into local memory, as a
+    //  separate function the call does; profiles/r2_c2_lanequeue.md.)
+    auto flush_saves = [&](bool final) {
+        __syncwarp();
+        const int n = (int)((qaddr - q0) / QSTRIDE);
+        int incl = n;
+        DEGK_UNROLL for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - n;
+        DEGK_UNROLL for (int k = 0; k < QDEPTH; ++k)
+            if (k < n) qdir[excl + k] = (unsigned short)(lane + 32u * (u32)k);
+        __syncwarp();
+        int done = 0;
+        while (total - done >= QBATCH || (final && done < total)) {
+            const int cnt = total - done < QBATCH ? total - done : QBATCH;
+            process_saves<T, Model, MethodS>(a, queue, qdir, done, cnt, sv_saddr);
+            done += cnt;
+        }
+        const int left = total - done;       // < QBATCH
+        Rec r[QBATCH / 32];
+        DEGK_UNROLL for (int j = 0; j < QBATCH / 32; ++j)
+            if ((int)lane + 32 * j < left) rec_copy(&r[j], queue + qdir[done + (int)lane + 32 * j]);
+        __syncwarp();
+        qaddr = q0;
+        DEGK_UNROLL for (int j = 0; j < QBATCH / 32; ++j)
+            if ((int)lane + 32 * j < left) { rec_copy(queue + lane + 32 * j, &r[j]); qaddr += QSTRIDE; }
+        __syncwarp();
+    };
+
+    bool service = true;                     // warp-uniform: a slot needs attention (or start of the kernel)
     u32 iter = 0;                            // warp-uniform pass counter
     bool all_done = false;
     bool started = false;                    // warp-uniform: the first service pass (initial fill) ran
     for (;;) {
         if (service) {
             u32 freshm = 0;
+            // some lane's part of the save queue is nearly full
+            if (__any_sync(0xffffffffu, qaddr >= qtrig)) flush_saves(false);
+            // maximum number of attempts reached: park the slot, the retire path reports MaxIters
+            DEGK_UNROLL for (int s = 0; s < W; ++s)
+                if (natt[s] >= max_it && h[s] >= dtmin) h[s] = kDead;
             for (;;) {
                 // slot states: integrating (h >= dtmin) / stopped, waiting to retire / free
                 u32 havem = 0, donem = 0;
@@ -385,15 +403,13 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
                 }
                 // several save points inside one accepted step: the queued record covers all of them
                 // (the replay loops), skip the cursor past them
-                // (after the push next_save is the old next_save2 and t the end of the step, so
-                //  `next_save <= t` after at least one accepted step identifies exactly those slots;
+                // (after the push next_save is the save time behind the pushed one and t the end of the step,
+                //  so `next_save <= t` after at least one accepted step identifies exactly those slots;
                 //  before the first accepted step a save point may legitimately lie before t0 -- it
                 //  is extrapolated from the first step like integrator_utils.jl:34-47 does)
                 DEGK_UNROLL for (int s = 0; s < W; ++s) {
                     if (next_save[s] <= t[s] && nacc[s] != 0u) {
-                        while (cur[s] <= nsv && save_time(cur[s]) <= t[s]) ++cur[s];
-                        next_save[s] = save_time(cur[s]);
-                        next_save2[s] = save_time(cur[s] + 1);
+                        do { ca[s] += (u32)sizeof(T); next_save[s] = lds_(ca[s], (T)0); } while (next_save[s] <= t[s]);   // ends at the +inf sentinel
                     }
                 }
                 // ---------------- retire stopped trajectories, in batches ----------------
@@ -424,7 +440,7 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
                             else if (natt_ >= max_it) rc = RC_MAXITERS;
                             else if (h[s] >= (T)0) rc = RC_DT_LESS_THAN_MIN;
                             else rc = RC_UNSTABLE;
-                            if (has_saveat && a.nsaved) a.nsaved[traj[s]] = cur[s] - 1;
+                            if (has_saveat && a.nsaved) a.nsaved[traj[s]] = cursor_of(ca[s]) - 1;
                             if (a.retcode) a.retcode[traj[s]] = rc;
                             if (a.naccept) a.naccept[traj[s]] = (int)nacc[s];
                             if (a.nreject) a.nreject[traj[s]] = (int)(natt_ - nacc[s]);
@@ -519,8 +535,8 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
             }
             const V ex = vclamp(fma_(V(-b1h), L, fma_(V(b2h), PO::make(lqe), V(k0))), exLo, exHi);
             const V hf = hv * vexp2(ex);                             // dt * fac
-            const V rem = (tfv - tv) - hv;                           // tf - t - dt
             const V tsum = tv + hv;
+            const V rem = tfv - tsum;                                // what is left after this step (exact when small)
             DEGK_UNROLL for (int s = 0; s < W; ++s) {
                 hf_[s] = PO::get(hf, s); rem_[s] = PO::get(rem, s); tsum_[s] = PO::get(tsum, s);
                 lqa_[s] = fmax_(PO::get(L, s), lqInit);
@@ -532,69 +548,74 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
                     const T sq = SM::scaled_sq(PO::get(u[c], s), PO::get(unew[c], s), PO::get(err[c], s), abstol, reltol);
                     accn = (c == 0) ? sq : accn + sq;
                 }
-                SM::control(accn, lq[s], h[s], rej[s], hf_[s], lqa_[s]);
+                SM::control(accn, lq[s], lqInit, h[s], rej[s], hf_[s], lqa_[s]);
                 rem_[s] = tf[s] - t[s] - h[s];
                 tsum_[s] = t[s] + h[s];
             }
         }
 
         // ---------------- per-slot flags ----------------
-        bool push[W], acc_[W], stop_[W];
+        bool push[W], acc_[W];
         T tnew_[W], hnext_[W];
         bool any_evt = false;
         DEGK_UNROLL for (int s = 0; s < W; ++s) {
-            // land on tf (gpu_tsit5_perform_step.jl:155-156); a step that cannot advance t
-            // (remaining span below ulp(t)) lands too -- the reference would loop forever
-            const bool land = (rem_[s] < MethodS::land()) | ((tsum_[s] == t[s]) & (rem_[s] <= h[s]));
+            bool land;
+            T hacc;
+            if constexpr (FAST) {
+                // rem = tf - (t + dt): landing (gpu_tsit5_perform_step.jl:155-156) leaves a next step
+                // min(dt * fac, rem) < dtmin, i.e. the slot stops integrating by itself
+                land = rem_[s] < dtmin;
+                hacc = fmin_(hf_[s], rem_[s]);
+            } else {
+                // rem = tf - t - dt as the reference computes it; a step that cannot advance t (remaining span
+                // below ulp(t)) lands too -- the reference would loop forever
+                land = (rem_[s] < MethodS::land()) | ((tsum_[s] == t[s]) & (rem_[s] <= h[s]));
+                hacc = SM::next_h_accept(hf_[s], rem_[s]);
+            }
             const T tn = land ? tf[s] : tsum_[s];
-            if constexpr (FAST) hnext_[s] = rej[s] ? hf_[s] : fmin_(abs_(hf_[s]), abs_(rem_[s]));
-            else hnext_[s] = rej[s] ? hf_[s] : SM::next_h_accept(hf_[s], rem_[s]);
+            const T hn = rej[s] ? hf_[s] : hacc;
             const bool live = h[s] >= dtmin;                     // dead slots carry h < dtmin
             const bool ok = live & solved;                       // W factorised
             const bool accept = ok & !rej[s];
             inc_if(ok, natt[s]);
             inc_if(accept, nacc[s]);
-            const bool fin = accept & !(tn < tf[s]);
-            const bool many = natt[s] >= max_it;
             // (a step size below dtmin needs no test here: the slot is simply not live any more
             //  in the next iteration -- `dt < dtmin && error(...)` -- and retires as DtLessThanMin)
-            const bool mult = accept & (next_save2[s] <= tn);
             push[s] = accept & (next_save[s] <= tn);
-            acc_[s] = accept; stop_[s] = ok & (fin | many);
+            acc_[s] = accept;
             tnew_[s] = tn;
-            // a stopped slot just idles until the service path next looks (every DEGK4_SERVICE_PERIOD passes);
-            // only a step across several save points needs it at once (the cursor has to be moved on)
-            any_evt |= mult;
-            bool okh = ok;
+            // a slot that reached tf just idles until the service path next looks (every DEGK4_SERVICE_PERIOD
+            // passes); the attempt limit, a step across several save points (below) and a nearly full save
+            // queue need the service path at once
+            any_evt |= ok & (natt[s] >= max_it);
+            bool park = false;
+            if constexpr (!PARK_NATURAL) park = accept & !(tn < tf[s]);
             if (!MethodS::ALWAYS_SOLVED) {
                 const bool sing = live & !solved;
                 singm |= (u32)sing << s;
-                stop_[s] |= sing; okh |= sing;                   // park the slot (h = -1)
+                park |= sing;
             }
-            const T hn = stop_[s] ? kDead : hnext_[s];
-            hnext_[s] = okh ? hn : h[s];
+            hnext_[s] = live ? (park ? kDead : hn) : h[s];
         }
 
-        // ---------------- queue the deferred saves (branch-free) ----------------
-        {
-            int pos = qcount;
-            DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                const u32 pm = __ballot_sync(0xffffffffu, push[s]);
-                Rec r;
-                r.traj = traj[s];
-                r.cur = cur[s];
-                r.tprev = t[s];
-                r.h = h[s];
-                r.tnew = tnew_[s];
-                DEGK_UNROLL for (int c = 0; c < N; ++c) r.u[c] = PO::get(u[c], s);
-                rec_store_if(push[s], queue_saddr + (u32)(pos + __popc(pm & lt_mask)) * (u32)sizeof(Rec), r);
-                pos += __popc(pm);
-                inc_if(push[s], cur[s]);
-                next_save[s] = push[s] ? next_save2[s] : next_save[s];
-                next_save2[s] = save_time(cur[s] + 1);
-            }
-            qcount = pos;
+        // ---------------- queue the deferred saves (branch-free, lane-private) ----------------
+        DEGK_UNROLL for (int s = 0; s < W; ++s) {
+            Rec r;
+            r.traj = traj[s];
+            r.cur = ca[s];
+            r.tprev = t[s];
+            r.h = h[s];
+            r.tnew = tnew_[s];
+            DEGK_UNROLL for (int c = 0; c < N; ++c) r.u[c] = PO::get(u[c], s);
+            rec_store_if(push[s], qaddr, r);
+            add_if<QSTRIDE>(push[s], qaddr);
+            add_if<(u32)sizeof(T)>(push[s], ca[s]);
+            lds_if(push[s], ca[s], next_save[s]);
+            // several save points inside this step: the queued record covers all of them (the replay loops),
+            // the service path moves the cursor past them before the next attempt
+            any_evt |= push[s] & (next_save[s] <= tnew_[s]);
         }
+        any_evt |= qaddr >= qtrig;
 
         // ---------------- state update (selects only) ----------------
         DEGK_UNROLL for (int s = 0; s < W; ++s) {
@@ -607,29 +628,11 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
         DEGK_UNROLL for (int c = 0; c < N; ++c) assign_if(acc_, u[c], unew[c]);
         MethodV::accepted_if(K, acc_);
 
-        // ---------------- drain the save queue (after the commit: only the loop-carried state is live) ----------------
-        // (a loop, not an `if`: up to 32 * W records can arrive in one iteration; the queue is drained below
-        //  one batch before the next push)
-        while (qcount >= QBATCH) {
-            __syncwarp();
-            if constexpr (PREPLAY) process_saves_packed<Model, MethodV>(a, queue, qcount - QBATCH, QBATCH, sv_saddr);
-            else process_saves<T, Model, MethodS>(a, queue, qcount - QBATCH, QBATCH, sv_s);
-            qcount -= QBATCH;
-            __syncwarp();
-        }
-
         ++iter;
         service = __any_sync(0xffffffffu, any_evt) | ((iter & (u32)(DEGK4_SERVICE_PERIOD - 1)) == 0u);
     }
-    // flush the remaining deferred saves
-    __syncwarp();
-    while (qcount > 0) {
-        const int n = qcount < QBATCH ? qcount : QBATCH;
-        if constexpr (PREPLAY) process_saves_packed<Model, MethodV>(a, queue, qcount - n, n, sv_saddr);
-        else process_saves<T, Model, MethodS>(a, queue, qcount - n, n, sv_s);
-        qcount -= n;
-        __syncwarp();
-    }
+    // the remaining deferred saves
+    flush_saves(true);
     add_totals<T>(a, tot_acc, tot_rej, tot_fail);
 }
 

@@ -19,19 +19,11 @@
 #include "device/degk_models.cuh"
 #include "device/gen_erk_tsit5.cuh"
 #include "device/degk_ode_kernels.cuh"
-#include "../../tools/experiments/degk_ode_kernels2_round1.cuh"
-#include "../../tools/experiments/degk_ode_kernels3_round1.cuh"
-#if GEN >= 4
 #include "device/degk_ode_kernels4.cuh"
-#endif
-#if GEN >= 5
-#include "../../tools/experiments/degk_ode_kernels5.cuh"   // two-stream variant (measured slower; kept as an experiment)
-#endif
 #include "degk_internal.h"
 
-#ifndef GEN
-#define GEN 3
-#endif
+#undef GEN
+#define GEN 4
 #ifndef MINBLOCKS
 #define MINBLOCKS 4
 #endif
@@ -43,15 +35,7 @@ using namespace degk;
 template <class T, class Model, template <class, class> class Method, int W>
 __global__ void __launch_bounds__(DEGK_BLOCK2, MINBLOCKS) k_probe(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) unsigned char degk_smem[];
-#if GEN >= 5
-    ode_asolve5_body<T, Model, Method, W>(a, degk_smem);
-#elif GEN >= 4
     ode_asolve4_body<T, Model, Method, W>(a, degk_smem);
-#elif GEN == 3 && !DEGK_STRICT
-    ode_asolve3_body<T, Model, Method, W>(a, degk_smem);
-#else
-    ode_asolve2_body<T, Model, Method, W>(a, degk_smem);
-#endif
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); exit(1); } } while (0)
@@ -68,6 +52,7 @@ int main(int argc, char** argv) {
     const int with_stats = argc > 4 ? atoi(argv[4]) : 0;      // retcode / naccept / nreject arrays
     const int sched = argc > 5 ? atoi(argv[5]) : 1;           // 0 static, 1 queue
     const int sorted = argc > 6 ? atoi(argv[6]) : 0;          // 1: start order sorted by rho (p[1])
+    const int retire_batch = argc > 7 ? atoi(argv[7]) : 0;    // 0: the kernel's default
     constexpr int W = WSLOTS;
     typedef float T;
     const int nsv = 11;
@@ -100,23 +85,16 @@ int main(int argc, char** argv) {
     KArgs k; memset(&k, 0, sizeof k);
     k.n_traj = N; k.u0 = du0; k.u0_stride = 0; k.p = dp; k.p_stride = 3; k.tspan = dtspan; k.tspan_stride = 0;
     k.saveat = dsv; k.n_saveat = nsv; k.n_rows = nsv; k.us = dus; k.ts = dts; k.out_layout = LAYOUT_REF; k.schedule = sched ? SCHED_QUEUE : SCHED_STATIC;
-#if GEN >= 4
     k.order = dorder;
-#endif
     k.retcode = drc; k.naccept = dna; k.nreject = dnr; k.nsaved = dns;
-    k.dt = 0.1f; k.abstol = 1e-6f; k.reltol = 1e-6f; k.totals = dtot; k.work_counter = dctr; k.max_iters = 10000000;
+    k.dt = 0.1f; k.abstol = 1e-6f; k.reltol = 1e-6f; k.totals = dtot; k.work_counter = dctr; k.max_iters = 10000000; k.retire_batch = retire_batch;
 
     auto kern = k_probe<T, Lorenz, ErkTsit5, W>;
-#if GEN >= 4
     const size_t smem = asolve4_smem_bytes<T, Lorenz::N, Lorenz::NP, W>(DEGK_BLOCK2 / 32, nsv);
-#else
-    const size_t nw = DEGK_BLOCK2 / 32;
-    const size_t smem = nw * asolve2_qcap<T, 3, W>() * sizeof(SaveRec<T, 3>) + nw * 32 * (3 + 3 + 2) * sizeof(T) + (nsv + 2) * sizeof(T);
-#endif
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DEGK_BLOCK2, smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-    const int per_thread = GEN >= 5 ? 2 * W : W;
+    const int per_thread = W;
     long long blocks = (N + DEGK_BLOCK2 * per_thread - 1) / (DEGK_BLOCK2 * per_thread);
     const long long resident = (long long)prop.multiProcessorCount * occ;
     if (sched && blocks > resident) blocks = resident;
