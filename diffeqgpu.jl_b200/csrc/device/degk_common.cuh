@@ -84,6 +84,14 @@ template <class T> DEGK_DEV T jl_min(T a, T b) {
     return a < b ? a : b;
 #endif
 }
+#if DEGK_STRICT
+// Float32: the NaN-propagating forms are single instructions (FMNMX.NAN) instead of three compares and three
+// selects.  Same value as the generic form for every operand pair the steppers produce (the operands are
+// magnitudes or positive step-size factors, so the +0 / -0 ordering of max.NaN never matters); a NaN result may
+// carry the other operand's payload, which no output ever shows.
+template <> DEGK_DEV float jl_max<float>(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+template <> DEGK_DEV float jl_min<float>(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+#endif
 DEGK_DEV float  abs_(float x)  { return fabsf(x); }
 DEGK_DEV double abs_(double x) { return fabs(x); }
 DEGK_DEV float  sqrt_(float x)  { return sqrtf(x); }     // IEEE (-prec-sqrt=true default)
