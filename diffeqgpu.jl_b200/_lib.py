@@ -18,7 +18,8 @@ FP_STRICT, FP_FAST = 0, 1
 LAYOUT_REF, LAYOUT_SOA = 0, 1
 SCHED_STATIC, SCHED_QUEUE, SCHED_AUTO = 0, 1, 2
 NOISE_NONE, NOISE_DIAGONAL, NOISE_GENERAL = 0, 1, 2
-ENGINE_AUTO, ENGINE_V1 = 0, 1
+ENGINE_AUTO, ENGINE_V1, ENGINE_LOCKSTEP = 0, 1, 2
+ENGINES = {"auto": ENGINE_AUTO, "v1": ENGINE_V1, "lockstep": ENGINE_LOCKSTEP}
 RETCODES = {0: "Default", 1: "Success", 2: "DtLessThanMin", 3: "Unstable", 4: "MaxIters",
             5: "Singular", 6: "Terminated", 7: "InitialFailure"}
 

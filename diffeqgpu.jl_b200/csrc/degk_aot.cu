@@ -19,6 +19,7 @@
 #include "device/degk_kvaerno.cuh"
 #include "device/degk_ode_kernels.cuh"
 #include "device/degk_ode_kernels4.cuh"
+#include "device/degk_ode_lockstep.cuh"
 #include "device/degk_sde_kernels.cuh"
 #include "degk_internal.h"
 
@@ -43,6 +44,11 @@ __global__ void __launch_bounds__(DEGK_BLOCK2, (asolve4_minblocks<T, Method<T, M
     extern __shared__ __align__(16) unsigned char degk_smem[];
     ode_asolve4_body<T, Model, Method, W>(a, degk_smem);
 }
+template <int FPMODE, class T, class Model, template <class, class> class Method, int W>
+__global__ void __launch_bounds__(DEGK_BLOCK2, (lockstep_minblocks<T>())) k_ode_lockstep(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char degk_smem[];
+    ode_solve_lockstep_body<T, Model, Method, W>(a, degk_smem);
+}
 template <int FPMODE, class T, class Model, int ALG>
 __global__ void __launch_bounds__(DEGK_BLOCK) k_sde_solve(const KArgs a) {
     sde_solve_body<T, Model, ALG>(a);
@@ -64,11 +70,12 @@ using namespace degk;
     (const void*)&k_ode_asolve2<DEGK_STRICT, T, MD, METHOD, W>, W, asolve4_qcap<T, MD::N, W>(),     \
         (int)sizeof(SaveRec<T, MD::N>)
 #define NOV2 nullptr, 0, 0, 0
+#define LS(T, MD, METHOD, W) (const void*)&k_ode_lockstep<DEGK_STRICT, T, MD, METHOD, W>, W
 // explicit RK: packed pairs for Float32 in fast mode
 #define ODE_ERK(NAME, MD, METHOD, ALG)                                                              \
-    {NAME, ALG, 0, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, float, MD, METHOD>, NOV2},    \
+    {NAME, ALG, 0, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, float, MD, METHOD>, NOV2, LS(float, MD, METHOD, WF32)},    \
     {NAME, ALG, 0, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, float, MD, METHOD>, V2(float, MD, METHOD, WF32)}, \
-    {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, double, MD, METHOD>, NOV2},   \
+    {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, double, MD, METHOD>, NOV2, LS(double, MD, METHOD, 1)},   \
     {NAME, ALG, 1, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, double, MD, METHOD>, V2(double, MD, METHOD, 1)},
 // Rosenbrock: packed pairs too while the linear solve is the closed form (n <= 3: products, sums and one
 // reciprocal of the determinant); the pivoting LU of larger systems compares values and stays scalar

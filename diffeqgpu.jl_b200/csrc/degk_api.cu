@@ -193,6 +193,7 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
         } else {
             prog->fn[0] = e0->fn;
             prog->fn[1] = e1 ? e1->fn : nullptr;
+            if (e0->fn3) { prog->fn[3] = e0->fn3; prog->w3 = e0->w3; }
             if (e1 && e1->fn2) {
                 prog->fn[2] = e1->fn2;
                 prog->w2 = e1->w2; prog->qcap2 = e1->qcap2; prog->rec_bytes2 = e1->rec_bytes2;
@@ -403,15 +404,38 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     const bool v2 = which == 1 && a->engine != DEGK_ENGINE_V1 && prog->info.slots_per_thread2 > 0 && !prog->has_events &&
                     stageable && (prog->info.is_jit ? prog->jit_fn[2] != nullptr : prog->fn[2] != nullptr);
     if (prog->has_events) sched = k.schedule = DEGK_SCHED_STATIC;   // one thread per trajectory
-    const int block = v2 ? DEGK_BLOCK2 : DEGK_BLOCK;
-    const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : DEGK_BLOCK;
+    // fixed dt, one (t0, tf, dt) for the whole launch, every-step saves, explicit RK stepper: the lock-step kernel
+    // (degk_ode_lockstep.cuh).  By default only for launches that fill the GPU with it -- with a few warps per SM
+    // the run is latency-bound and one trajectory per thread on more SMs is faster (C1 at N = 10^4).
+    const bool has_ls = prog->info.is_jit ? prog->jit_fn[3] != nullptr : prog->fn[3] != nullptr;
+    const bool ls = which == 0 && has_ls && !prog->is_sde && !prog->has_events && a->engine != DEGK_ENGINE_V1 && !a->saveat &&
+                    a->save_everystep && a->tspan_stride == 0 && !a->dae_init && a->n_tstops == 0 && !a->reduce &&
+                    (a->engine == DEGK_ENGINE_LOCKSTEP || a->n_traj >= (long long)ctx->sm_count * DEGK_BLOCK2 * prog->w3 * 2) &&
+                    !getenv("DEGK_NO_LOCKSTEP");
+    const int block = (v2 || ls) ? DEGK_BLOCK2 : DEGK_BLOCK;
+    const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : (ls ? DEGK_BLOCK2 * prog->w3 : DEGK_BLOCK);
     size_t smem = 0;
     if (v2) smem = degk_smem2_bytes(prog, a->saveat ? a->n_saveat : 0);
+    if (ls) {
+        // reference layout: R rows per trajectory staged in shared memory (<= 48 KB per block) and flushed coalesced;
+        // the trajectory-major layout needs no staging (lanes already write consecutive addresses)
+        const size_t es = dtype_size(prog->info.dtype);
+        const int n = prog->info.n_state;
+        if (a->out_layout == DEGK_LAYOUT_REF) {
+            const int words_per_thread = (int)(48 * 1024 / (DEGK_BLOCK2 * es));
+            int R = (words_per_thread / prog->w3 - 2) / n;
+            if (R > 16) R = 16;
+            if (R >= 2) {
+                k.stage_rows = R;
+                smem = (size_t)(DEGK_BLOCK2 / 32) * ((size_t)32 * prog->w3 * (size_t)((n * R) | 1) + (size_t)R) * es;   // lockstep_smem_bytes
+            }
+        }
+    }
     // fixed-dt kernel, every-step saves in the reference layout: stage R rows per lane in shared
     // memory (<= 48 KB per block, so no opt-in attribute is needed) and flush them coalesced
     // (only when the launch fills the GPU: with a few warps per SM the kernel is latency-bound and the
     //  serial flush costs more than the scattered stores -- C1 at N = 10^4: 0.15 ms direct, 0.22 ms staged)
-    if (which == 0 && !prog->is_sde && !prog->has_events && !a->saveat && a->save_everystep &&
+    if (!ls && which == 0 && !prog->is_sde && !prog->has_events && !a->saveat && a->save_everystep &&
         a->out_layout == DEGK_LAYOUT_REF && a->n_traj >= (long long)ctx->sm_count * DEGK_BLOCK * 3 &&
         !getenv("DEGK_NO_STAGED_SAVES")) {
         const size_t es = dtype_size(prog->info.dtype);
@@ -434,7 +458,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     }
     if (blocks > 2147483647LL) { degk_set_error(ctx, "too many blocks"); return DEGK_ERR_INVALID; }
 
-    const int kidx = v2 ? 2 : which;
+    const int kidx = v2 ? 2 : (ls ? 3 : which);
     int rc = DEGK_OK;
     if (prog->info.is_jit) {
         rc = degk_jit_launch(prog, kidx, (unsigned)blocks, (unsigned)block, (unsigned)smem, &k, stream);

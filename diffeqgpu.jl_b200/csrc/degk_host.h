@@ -39,10 +39,12 @@ struct degk_program {
     degk_program_info info;
     bool is_sde = false;
     bool has_events = false;                  // built with the tstops / callback kernel pair (degk_ode_events.cuh)
-    const void* fn[3] = {nullptr, nullptr, nullptr};   // AOT kernels: [0] fixed-dt / SDE, [1] adaptive v1, [2] adaptive v2
+    // AOT kernels: [0] fixed-dt / SDE, [1] adaptive v1, [2] adaptive v2, [3] lock-step fixed-dt
+    const void* fn[4] = {nullptr, nullptr, nullptr, nullptr};
     int w2 = 0, qcap2 = 0, rec_bytes2 = 0;             // geometry of the v2 kernel (see degk_internal.h)
+    int w3 = 0;                               // trajectories per thread of the lock-step kernel
     void* jit_module = nullptr;               // CUmodule
-    void* jit_fn[3] = {nullptr, nullptr, nullptr};     // CUfunction, same indexing as fn
+    void* jit_fn[4] = {nullptr, nullptr, nullptr, nullptr};     // CUfunction, same indexing as fn
 };
 
 void degk_set_error(degk_ctx* ctx, const char* fmt, ...);

@@ -19,4 +19,7 @@ struct degk_aot_entry {
     int w2;         // trajectories per thread of fn2 (1 or 2)
     int qcap2;      // save-queue capacity per warp (records)
     int rec_bytes2; // sizeof(SaveRec<T, N>)
+    // lock-step fixed-dt kernel (degk_ode_lockstep.cuh): uniform (t0, tf, dt), every-step saves; null if none
+    const void* fn3;
+    int w3;         // trajectories per thread of fn3 (1 or 2)
 };

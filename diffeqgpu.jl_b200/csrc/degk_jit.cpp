@@ -208,7 +208,7 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
     }
     src += is_sde ? "#include \"degk_sde_kernels.cuh\"\n"
            : events ? "#include \"degk_ode_events.cuh\"\n"
-                    : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels4.cuh\"\n";
+                    : "#include \"degk_ode_kernels.cuh\"\n#include \"degk_ode_kernels4.cuh\"\n#include \"degk_ode_lockstep.cuh\"\n";
     snprintf(buf, sizeof buf, "typedef %s REAL;\n", d->dtype == DEGK_F64 ? "double" : "float");
     src += buf;
     if (d->rhs_src) {
@@ -382,6 +382,15 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                  "    degk::ode_asolve4_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
                  rec_bytes, slots, save_queue_cap(rec_bytes, slots), DEGK_BLOCK2, slots);
         src += buf;
+        if (d->alg == DEGK_ALG_TSIT5 || d->alg == DEGK_ALG_VERN7 || d->alg == DEGK_ALG_VERN9) {
+            // lock-step fixed-dt kernel (uniform tspan and dt, every-step saves): the explicit RK steppers only
+            snprintf(buf, sizeof buf,
+                     "extern \"C\" __global__ void __launch_bounds__(%d, (degk::lockstep_minblocks<REAL>())) degk_jit_lockstep(const degk::KArgs a) {\n"
+                     "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
+                     "    degk::ode_solve_lockstep_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
+                     DEGK_BLOCK2, slots);
+            src += buf;
+        }
     }
     return DEGK_OK;
 }
@@ -477,6 +486,12 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
         DRV(ctx, g_drv.ModuleGetFunction(&f2, mod, "degk_jit_adaptive2"));
     }
     prog->jit_fn[2] = f2;
+    if (!events && !is_sde && (d->alg == DEGK_ALG_TSIT5 || d->alg == DEGK_ALG_VERN7 || d->alg == DEGK_ALG_VERN9)) {
+        CUfunction f3 = nullptr;
+        DRV(ctx, g_drv.ModuleGetFunction(&f3, mod, "degk_jit_lockstep"));
+        prog->jit_fn[3] = f3;
+        prog->w3 = slots;
+    }
     prog->info.is_jit = 1;
     if (d->rhs_src) {
         const int noise = is_sde ? d->noise_kind : 0;

@@ -208,7 +208,7 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
             d_order = torch.argsort(key.reshape(-1)).to(torch.int32)
             a.order = d_order.data_ptr()
         a.max_iters = int(__import__("os").environ.get("DEGK_MAX_ITERS", "0"))   # 0 => library default (1e7 attempts per trajectory when adaptive, none for fixed dt)
-        a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
+        a.engine = _lib.ENGINES[engine]
         a.dae_init = int(bool(getattr(prob.f, "initialize", False))) if isinstance(prob, ODEProblem) else 0
         prog.solve(a, launch_stream.cuda_stream)
         for buf in (probs.u0, probs.p, probs.tspan, reduce):     # inputs made on other streams stay alive until this one is done
@@ -223,9 +223,11 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
 
 def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, debug=False,
                      callback=None, tstops=None, fp_mode="strict", schedule="auto", layout="ref",
-                     stats=False, stream=None, traj_offset=0, reduce=None, **kwargs):
+                     stats=False, stream=None, traj_offset=0, reduce=None, engine="auto", **kwargs):
     """Fixed-step batched solve; returns (ts, us) on the device (add `stats=True` for
-    per-trajectory retcode/naccept/nreject and totals, which the reference does not have)."""
+    per-trajectory retcode/naccept/nreject and totals, which the reference does not have).
+    `engine`: "auto" (the lock-step kernel for large launches with one tspan, every-step saves and an explicit RK
+    stepper, else one thread per trajectory), "lockstep" (whenever its preconditions hold), "v1" (never)."""
     if not isinstance(alg, GPUODEAlgorithm):
         raise TypeError("alg must be a GPUODEAlgorithm / GPUSDEAlgorithm")
     is_sde = isinstance(prob, SDEProblem)
@@ -254,7 +256,7 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
     return _launch(probs, prob, alg, dt=dt, adaptive=False, abstol=0.0, reltol=0.0, saveat=saveat_c,
                    save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
                    schedule=schedule, layout=layout, stats=stats, stream=stream,
-                   traj_offset=traj_offset, reduce=reduce, callback=callback, tstops=tstops)
+                   traj_offset=traj_offset, reduce=reduce, callback=callback, tstops=tstops, engine=engine)
 
 
 def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save_everystep=False,

@@ -236,7 +236,7 @@ def solve_host(prob, alg, *, u0=None, p=None, tspan=None, n_traj=None, dt, adapt
     a.out_layout = _lib.LAYOUT_REF if layout == "ref" else _lib.LAYOUT_SOA
     a.schedule = SCHEDULES[schedule]
     a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    a.engine = _lib.ENGINE_V1 if engine == "v1" else _lib.ENGINE_AUTO
+    a.engine = _lib.ENGINES[engine]
     st = {}
     if stats == "totals":      # only the 4 global counters: no per-trajectory arrays to download
         st = dict(totals=np.zeros(4, np.uint64))

@@ -93,8 +93,12 @@ typedef enum {
 
 /* DEGK_ENGINE_AUTO picks the second-generation adaptive kernel (batched deferred saves, two
  * trajectories per thread in FFMA2 register pairs for Float32 fast mode) when the program has
- * one; DEGK_ENGINE_V1 forces the first-generation kernel (kept for A/B measurements). */
-typedef enum { DEGK_ENGINE_AUTO = 0, DEGK_ENGINE_V1 = 1 } degk_engine;
+ * one, and for fixed-dt runs the lock-step kernel (uniform tspan and dt, every-step saves, explicit
+ * RK stepper; two trajectories per thread in the Float32 fast mode) when the launch is large enough
+ * to fill the GPU with it; DEGK_ENGINE_V1 forces the first-generation kernels (one thread per
+ * trajectory; kept for A/B measurements); DEGK_ENGINE_LOCKSTEP takes the lock-step kernel whenever
+ * its preconditions hold, whatever the launch size. */
+typedef enum { DEGK_ENGINE_AUTO = 0, DEGK_ENGINE_V1 = 1, DEGK_ENGINE_LOCKSTEP = 2 } degk_engine;
 
 typedef enum { DEGK_NOISE_NONE = 0, DEGK_NOISE_DIAGONAL = 1, DEGK_NOISE_GENERAL = 2 } degk_noise;
 
