@@ -73,6 +73,14 @@ size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged) {
            ((size_t)n_saveat_staged + 2) * es;     // + two +inf sentinels
 }
 
+// dynamic shared memory of the lock-step kernel in the reference layout (degk_ode_lockstep.cuh, lockstep_smem_bytes):
+// per warp 32 w buffers of 32 / w rows (rounded up to a multiple of four values, plus four) and the ring of save times
+size_t degk_lockstep_smem_bytes(const degk_program* prog) {
+    const size_t es = dtype_size(prog->info.dtype);
+    const int rows = 32 / std::max(1, prog->w3);                  // lockstep_ring_rows
+    return (size_t)(DEGK_BLOCK2 / 32) * ((size_t)32 * prog->w3 * (size_t)(((prog->info.n_state * rows + 3) & ~3) + 4) + (size_t)rows) * es;
+}
+
 extern "C" int degk_version(void) { return DEGK_VERSION; }
 
 extern "C" const char* degk_last_error(degk_ctx* ctx) {
@@ -217,6 +225,11 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
             const void* fo = prog->fn[1] ? prog->fn[1] : prog->fn[0];
             CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fo, DEGK_BLOCK, 0));
             prog->info.max_blocks_per_sm = occ;
+            if (prog->fn[3]) {
+                const size_t ls_smem = degk_lockstep_smem_bytes(prog);
+                if (ls_smem > 48 * 1024 && ls_smem <= 64 * 1024)
+                    CK(ctx, cudaFuncSetAttribute(prog->fn[3], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+            }
             if (prog->fn[2]) {
                 cudaFuncAttributes fa;
                 CK(ctx, cudaFuncGetAttributes(&fa, prog->fn[2]));
@@ -417,18 +430,13 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     size_t smem = 0;
     if (v2) smem = degk_smem2_bytes(prog, a->saveat ? a->n_saveat : 0);
     if (ls) {
-        // reference layout: R rows per trajectory staged in shared memory (<= 48 KB per block) and flushed coalesced;
-        // the trajectory-major layout needs no staging (lanes already write consecutive addresses)
-        const size_t es = dtype_size(prog->info.dtype);
-        const int n = prog->info.n_state;
-        if (a->out_layout == DEGK_LAYOUT_REF) {
-            const int words_per_thread = (int)(48 * 1024 / (DEGK_BLOCK2 * es));
-            int R = (words_per_thread / prog->w3 - 2) / n;
-            if (R > 16) R = 16;
-            if (R >= 2) {
-                k.stage_rows = R;
-                smem = (size_t)(DEGK_BLOCK2 / 32) * ((size_t)32 * prog->w3 * (size_t)((n * R) | 1) + (size_t)R) * es;   // lockstep_smem_bytes
-            }
+        // reference layout: a 32 / w-row buffer per trajectory in shared memory, flushed in sector-aligned pieces
+        // (degk_ode_lockstep.cuh); the trajectory-major layout needs no staging (lanes already write consecutive
+        // addresses), and states too large for the rings go out unstaged as well
+        const size_t ring_bytes = degk_lockstep_smem_bytes(prog);
+        if (a->out_layout == DEGK_LAYOUT_REF && ring_bytes <= 64 * 1024) {
+            k.stage_rows = 16;
+            smem = ring_bytes;
         }
     }
     // fixed-dt kernel, every-step saves in the reference layout: stage R rows per lane in shared

@@ -49,6 +49,7 @@ struct degk_program {
 
 void degk_set_error(degk_ctx* ctx, const char* fmt, ...);
 size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged);
+size_t degk_lockstep_smem_bytes(const degk_program* prog);
 
 // NVRTC path (degk_jit.cpp)
 int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog);

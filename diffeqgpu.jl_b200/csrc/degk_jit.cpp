@@ -491,6 +491,11 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
         DRV(ctx, g_drv.ModuleGetFunction(&f3, mod, "degk_jit_lockstep"));
         prog->jit_fn[3] = f3;
         prog->w3 = slots;
+        prog->info.dtype = d->dtype;
+        prog->info.n_state = d->rhs_src ? d->n_state : builtin_n_state(d->builtin);
+        const size_t ls_smem = degk_lockstep_smem_bytes(prog);
+        if (ls_smem > 48 * 1024 && ls_smem <= 64 * 1024)
+            DRV(ctx, g_drv.FuncSetAttribute(f3, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)ls_smem));
     }
     prog->info.is_jit = 1;
     if (d->rhs_src) {

@@ -11,10 +11,14 @@
 //     h-scaled stage sums of the generated steppers, the strict build one trajectory with the reference's un-fused
 //     arithmetic (bit-identical to ode_solve_body, which the oracle pins);
 //   * the loop is unrolled twice so that u / unew swap roles instead of being copied;
-//   * in the reference layout the rows are staged in shared memory, R steps at a time, as one strip per trajectory
-//     and written out by the whole warp as one flattened copy (consecutive lanes = consecutive words); the save
-//     times are the same for every trajectory, so they are staged once per warp, not once per lane; the flush
-//     points of the warps are staggered so that stores and arithmetic overlap across the GPU.
+//   * in the reference layout every trajectory owns a contiguous strip of `us` (len * n values) at an arbitrary
+//     4-byte alignment, and what bounds the kernel is how the memory system digests the stores (measured: with the
+//     stores removed the rest runs 2.2x faster; pieces that end inside a 32-byte sector make the L2 fetch the sector
+//     from DRAM).  So the rows go through a 16- or 32-row buffer per trajectory in shared memory, and every 8 / 24
+//     steps the warp writes, for each trajectory, the words up to THAT trajectory's last sector boundary -- whole
+//     sectors, 16-byte loads and stores, four trajectories per instruction -- and the owning lane moves the few
+//     words behind the boundary to the front of the buffer.  Only the first and the last piece of a trajectory are
+//     ragged.  The save times are the same for every trajectory: one ring per warp.
 // Semantics kept from the reference: row 0 is prob.u0, integ.t += dt precedes the stages, the loop runs while
 // t < tf, a last step that overshoots tf is followed by the interpolated value at tf in the last row
 // (kernels.jl:53-57), rows past `len` are dropped, unwritten ts rows keep t0.
@@ -29,9 +33,90 @@ template <class M> struct lockstep_ok_of<M, typename replay_void_<decltype(M::LO
 
 template <class T> __host__ __device__ constexpr int lockstep_minblocks() { return sizeof(T) == 4 ? 4 : 1; }
 
-// shared memory per block: per warp 32 W strips of (N R) | 1 words (odd: lanes hit distinct banks), then R save times
-__host__ __device__ constexpr size_t lockstep_smem_bytes(int nwarps, int n, int w, int rows, size_t es) {
-    return (size_t)nwarps * ((size_t)32 * w * (size_t)((n * rows) | 1) + (size_t)rows) * es;
+// Rows a trajectory can buffer: 32 with one trajectory per thread, 16 with two (the same ~53 KB per block for a
+// three-component Float32 state).  A flush comes every (rows - 8) steps -- at most 7 left-over rows of the save times
+// plus (rows - 8 + 1) new ones fit -- so the one-trajectory builds, which are issue-bound, amortise the per-trajectory
+// part of a flush over three times as many rows.
+__host__ __device__ constexpr int lockstep_ring_rows(int w) { return 32 / w; }
+// words between the buffers of two trajectories: the rows, rounded up to a multiple of four words plus four (16-byte
+// aligned for the vector loads of the flush, and not a multiple of 32 banks)
+__host__ __device__ constexpr int lockstep_buf_words(int n, int w) { return ((n * lockstep_ring_rows(w) + 3) & ~3) + 4; }
+// shared memory per block: per warp 32 W buffers, then the ring of save times (one entry per buffered row)
+__host__ __device__ constexpr size_t lockstep_smem_bytes(int nwarps, int n, int w, size_t es) {
+    return (size_t)nwarps * ((size_t)32 * w * (size_t)lockstep_buf_words(n, w) + (size_t)lockstep_ring_rows(w)) * es;
+}
+
+// Sector-aligned window of one trajectory at a flush, in words relative to the trajectory's first word (NW words per
+// row): `phi` = (absolute word index of the trajectory's first word) mod (words per sector), so relative word r sits on a
+// sector boundary when (r + phi) is a multiple of SW.  F = what earlier flushes reached (the last boundary not beyond
+// row kpr, or 0), E = where this one ends (the last boundary not beyond row khi; row khi itself when `final`),
+// [Fa, Ea) = the whole sectors in between, [F, Fa) the ragged first words of a trajectory (F = 0 off a boundary),
+// [Ea, E) the ragged last ones (`final`).  F of a flush equals E of the one before by construction.
+template <int SW>
+DEGK_DEV void lockstep_window(int phi, int wpr, int whi, bool final, int& F, int& Fa, int& Ea, int& E) {
+    F = ((wpr + phi) & ~(SW - 1)) - phi;
+    F = F > 0 ? F : 0;
+    const int Ef = ((whi + phi) & ~(SW - 1)) - phi;
+    E = final ? whi : (Ef > F ? Ef : F);
+    Fa = ((F + phi + SW - 1) & ~(SW - 1)) - phi;                  // first boundary at or after F (F itself unless F = 0 is off one)
+    Fa = Fa < E ? Fa : E;
+    Ea = ((E + phi) & ~(SW - 1)) - phi;                           // last boundary at or before E
+    Ea = Ea > Fa ? Ea : Fa;
+}
+
+// Flush one output array for every trajectory of the warp (warp-collective; LPS lanes serve one trajectory): the whole
+// sectors of the window go out as 16-byte stores, the ragged first words of a trajectory (first flush) and last words
+// (`final`) one by one.  LINEAR: trajectory j has its own buffer at buf0 + j * stride whose word 0 is relative word F
+// (the owning lane compacts what is left after every flush), so in steady state the reads are 16-byte loads too;
+// otherwise buf0 is one ring of RING rows shared by all trajectories (the save times: position = row mod RING).
+// Not inlined: one copy per array kind keeps the time loop inside the instruction cache.
+template <class T, int NW, int LPS, bool LINEAR, int RING>
+__device__ __noinline__ void lockstep_flush_array(T* base, const T* buf0, int stride, i64 warp_first, int nstrips,
+                                                  i64 n_rows, i64 k_prev, i64 k_hi, bool final) {
+    constexpr int SW = 32 / (int)sizeof(T);                       // words per 32-byte sector
+    constexpr int QW = 16 / (int)sizeof(T);                       // words per 16-byte store
+    constexpr int PER_IT = 32 / LPS;
+    static_assert(LINEAR || NW == 1, "the shared ring holds one word per row");
+    const int lane = (int)lane_id();
+    const i64 khi = k_hi < n_rows ? k_hi : n_rows;                // rows past `len` are dropped
+    const i64 kpr = k_prev < khi ? k_prev : khi;
+    const int wpr = (int)kpr * NW, whi = (int)khi * NW;           // relative words reached before / now
+    const int sub = lane / LPS, q0 = lane % LPS;
+    const i64 row_words = n_rows * NW;
+    T* tb = base + (warp_first + sub) * row_words;                // first word of this lane's trajectory
+    const int rw = (int)(row_words & (SW - 1));
+    int phi = (int)((((unsigned long long)base / sizeof(T)) + (unsigned long long)((warp_first + sub) * row_words)) & (unsigned long long)(SW - 1));
+    const T* bj = buf0 + (size_t)sub * stride;
+    for (int j = sub; j < nstrips; j += PER_IT, tb += PER_IT * row_words, bj += PER_IT * stride, phi = (phi + PER_IT * rw) & (SW - 1)) {
+        int F, Fa, Ea, E;
+        lockstep_window<SW>(phi, wpr, whi, final, F, Fa, Ea, E);
+        auto word = [&](int r) -> T { return LINEAR ? bj[r - F] : bj[(r / NW) & (RING - 1)]; };   // relative word r
+        const int nq = (Ea - Fa) / QW;
+        T* dst = tb + Fa + q0 * QW;
+        _Pragma("unroll 1")                                       // at most one trip per lane except at the first flush
+        for (int q = q0; q < nq; q += LPS, dst += LPS * QW) {
+            const int r = Fa + q * QW;
+            uint4 pk;
+            if (LINEAR && Fa == F) {                              // steady state: the buffer starts on the boundary
+                pk = *reinterpret_cast<const uint4*>(bj + q * QW);
+            } else {
+                T v[QW];
+                DEGK_UNROLL for (int i = 0; i < QW; ++i) v[i] = word(r + i);
+                if constexpr (sizeof(T) == 4) {
+                    pk = make_uint4(__float_as_uint((float)v[0]), __float_as_uint((float)v[1]), __float_as_uint((float)v[QW - 2]), __float_as_uint((float)v[QW - 1]));
+                } else {
+                    const unsigned long long l0 = (unsigned long long)__double_as_longlong((double)v[0]), l1 = (unsigned long long)__double_as_longlong((double)v[QW - 1]);
+                    pk = make_uint4((unsigned)l0, (unsigned)(l0 >> 32), (unsigned)l1, (unsigned)(l1 >> 32));
+                }
+            }
+            *reinterpret_cast<uint4*>(dst) = pk;
+        }
+        // ragged head [F, Fa) of a trajectory's first piece and tail [Ea, E) of its last: fewer than SW words each
+        _Pragma("unroll 1")
+        for (int r = F + q0; r < Fa; r += LPS) tb[r] = word(r);
+        _Pragma("unroll 1")
+        for (int r = Ea + q0; r < E; r += LPS) tb[r] = word(r);
+    }
 }
 
 // STAGED: rows go through shared memory (reference layout); otherwise straight to `us` / `ts`.  Two instantiations of
@@ -64,27 +149,69 @@ DEGK_DEV void ode_solve_lockstep_run(const KArgs& a, unsigned char* smem_raw) {
         DEGK_UNROLL for (int s = 0; s < W; ++s) load_problem<T, Model>(a, valid[s] ? traj[s] : warp_first, us_[s], ps_[s], t0, tf);
         DEGK_UNROLL for (int c = 0; c < N; ++c) { T x[W]; DEGK_UNROLL for (int s = 0; s < W; ++s) x[s] = us_[s][c]; ua[c] = PO::make(x); ub[c] = ua[c]; }
         DEGK_UNROLL for (int c = 0; c < Model::NP; ++c) { T x[W]; DEGK_UNROLL for (int s = 0; s < W; ++s) x[s] = ps_[s][c]; p[c] = PO::make(x); }
-        DEGK_UNROLL for (int s = 0; s < W; ++s)
-            if (valid[s]) { store_u<T, N>(a, traj[s], 0, us_[s]); store_t<T>(a, traj[s], 0, t0); }     // row 0 = prob.u0
+        if constexpr (!STAGED) {
+            DEGK_UNROLL for (int s = 0; s < W; ++s)
+                if (valid[s]) { store_u<T, N>(a, traj[s], 0, us_[s]); store_t<T>(a, traj[s], 0, t0); } // row 0 = prob.u0
+        }
     }
     const T dt = (T)a.dt;
     const V dtv = V(dt);
 
-    // staging buffers of this warp
-    const int R = a.stage_rows;
-    const int S = (N * R) | 1;                                    // words per strip (odd: conflict-free column access)
-    T* wu = (T*)smem_raw + (size_t)(threadIdx.x >> 5) * ((size_t)32 * W * S + R);
+    // ---- staged saves (reference layout): rings in shared memory, sector-aligned flushes ----
+    constexpr int RING = lockstep_ring_rows(W), PERIOD = RING - 8;
+    constexpr int S = lockstep_buf_words(N, W);                   // words between the buffers of two trajectories
+    constexpr int SW = 32 / (int)sizeof(T);                       // words per 32-byte sector
+    T* wu = (T*)smem_raw + (size_t)(threadIdx.x >> 5) * ((size_t)32 * W * S + RING);
     T* wt = wu + (size_t)32 * W * S;
-    int nbuf = 0;                                                 // rows staged (warp-uniform)
-    i64 k0 = 1;                                                   // row of the first staged step
-    // Every warp of the launch runs the same loop in the same rhythm, so with a common flush period the whole GPU
-    // would alternate between compute-only and store-only phases (measured on C1 at 10^6: the store bursts added
-    // ~0.5 ms to 0.6 ms of compute).  The first flush of warp w comes after 1 + (w mod R) rows: at any time 1/R of
-    // the warps are storing while the others compute.
-    int room = STAGED ? 1 + (int)((warp_first / (32 * W)) % R) : 0;   // rows until the next flush
-    T* srow[W];                                                   // where this lane stages the next row of its trajectories
-    DEGK_UNROLL for (int s = 0; s < W; ++s) srow[s] = wu + (size_t)(lane + 32 * s) * S;
-    // unstaged saves (trajectory-major layout): per-slot output pointers that advance by one row per step
+    i64 k_prev = 0, k_hi = 0;                                     // rows [0, k_prev) were offered to a flush, [k_prev, k_hi) are new
+    // Every warp of the launch runs the same loop in the same rhythm; the first flush of warp w comes after
+    // 7 + (w mod PERIOD) rows (row 0 included that is at least 8 rows, so every trajectory has reached a sector
+    // boundary, and at most RING) and then every PERIOD: the warps store at different times.
+    int room = STAGED ? 7 + (int)((warp_first / (32 * W)) % PERIOD) : 0;   // rows until the next flush
+    T* fill[W];                                                   // where this lane stages the next row of its trajectories
+    int phis[W];                                                  // sector phase of their first words in `us`
+    DEGK_UNROLL for (int s = 0; s < W; ++s) {
+        fill[s] = wu + (size_t)(lane + 32 * s) * S;
+        phis[s] = (int)((((unsigned long long)a.us / sizeof(T)) + (unsigned long long)(traj[s] * a.n_rows * N)) & (unsigned long long)(SW - 1));
+    }
+
+    auto flush = [&](bool final) {
+        __syncwarp();
+        lockstep_flush_array<T, N, 8, true, RING>((T*)a.us, wu, S, warp_first, nstrips, a.n_rows, k_prev, k_hi, final);
+        if (a.ts != nullptr) lockstep_flush_array<T, 1, 4, false, RING>((T*)a.ts, wt, 0, warp_first, nstrips, a.n_rows, k_prev, k_hi, final);
+        __syncwarp();
+        if (!final) {
+            // every lane moves what its trajectories keep (the words behind their last sector boundary, fewer than
+            // a sector) to the front of their buffers
+            const i64 khi = k_hi < a.n_rows ? k_hi : a.n_rows, kpr = k_prev < khi ? k_prev : khi;
+            DEGK_UNROLL for (int s = 0; s < W; ++s) {
+                int F, Fa, Ea, E;
+                lockstep_window<SW>(phis[s], (int)kpr * N, (int)khi * N, false, F, Fa, Ea, E);
+                T* b = wu + (size_t)(lane + 32 * s) * S;
+                const int keep = (int)khi * N - E, off = E - F;
+                if (off > 0) {
+                    _Pragma("unroll 1")
+                    for (int i = 0; i < keep; ++i) b[i] = b[off + i];
+                }
+                fill[s] = b + keep;
+            }
+            __syncwarp();
+        }
+        k_prev = k_hi;
+    };
+    // stage row k_hi (state `v`, time `tt`) of every trajectory of this lane
+    auto stage_row = [&](const V (&v)[N], T tt) {
+        if (k_hi < a.n_rows) {                                    // rows past `len` are dropped
+            DEGK_UNROLL for (int s = 0; s < W; ++s) {
+                DEGK_UNROLL for (int c = 0; c < N; ++c) fill[s][c] = PO::get(v[c], s);
+                fill[s] += N;
+            }
+            if (lane == 0) wt[(int)(k_hi & (RING - 1))] = tt;
+        }
+        ++k_hi;
+    };
+
+    // ---- unstaged saves (trajectory-major layout): per-slot output pointers that advance by one row per step ----
     const bool soa = a.out_layout != LAYOUT_REF;
     const i64 ustep = soa ? (i64)N * a.n_traj : (i64)N;           // words between two rows of one trajectory
     const i64 ucomp = soa ? a.n_traj : 1;                         // words between two components of one row
@@ -95,59 +222,7 @@ DEGK_DEV void ode_solve_lockstep_run(const KArgs& a, unsigned char* smem_raw) {
         pu[s] = (T*)a.us + (soa ? traj[s] : traj[s] * a.n_rows * N) + ustep;                 // row 1
         pt[s] = a.ts ? (T*)a.ts + (soa ? traj[s] : traj[s] * a.n_rows) + tstep : nullptr;
     }
-
-    // Copy the staged [nstrips][n0 rows][N] block to the trajectories' strips of `us`: 32 consecutive words of one
-    // strip per store instruction (column passes over the strip, the warp walks down the strips), so the only
-    // address arithmetic in the loop is two constant increments.  The save times are the same for every strip; with
-    // at most 16 rows staged two strips share one store instruction.
-    auto flush = [&]() {
-        __syncwarp();
-        i64 n0 = a.n_rows - k0;                                   // rows past `len` are dropped
-        n0 = n0 < 0 ? 0 : (n0 < nbuf ? n0 : nbuf);
-        if (n0 > 0) {
-            const int L = (int)n0 * N;
-            const i64 rs = (i64)a.n_rows * N;
-            T* const obase = (T*)a.us + ((i64)warp_first * a.n_rows + k0) * N;
-            for (int w = (int)lane; w < L; w += 32) {
-                T* o = obase + w;
-                const T* sm = wu + w;
-                int j = 0;
-                // eight strips per batch: all loads first, then all stores (written out so that the eight values are
-                // live at once -- left to itself the compiler recycles four registers and serialises load -> store)
-                for (; j + 8 <= nstrips; j += 8) {
-                    T v[8];
-                    DEGK_UNROLL for (int q = 0; q < 8; ++q) v[q] = sm[q * S];
-                    DEGK_UNROLL for (int q = 0; q < 8; ++q) { *o = v[q]; o += rs; }
-                    sm += 8 * S;
-                }
-                for (; j < nstrips; ++j) { *o = *sm; o += rs; sm += S; }
-            }
-            if (a.ts != nullptr) {
-                const int nn = (int)n0;
-                T* const tbase = (T*)a.ts + (i64)warp_first * a.n_rows + k0;
-                if (nn <= 16) {
-                    const int half = (int)(lane >> 4), w = (int)(lane & 15u);
-                    if (w < nn) {
-                        const T v = wt[w];
-                        T* o = tbase + (i64)half * a.n_rows + w;
-                        const i64 two_rows = 2 * a.n_rows;
-                        _Pragma("unroll 4")
-                        for (int j = half; j < nstrips; j += 2) { *o = v; o += two_rows; }
-                    }
-                } else {
-                    for (int w = (int)lane; w < nn; w += 32) {
-                        const T v = wt[w];
-                        T* o = tbase + w;
-                        for (int j = 0; j < nstrips; ++j) { *o = v; o += a.n_rows; }
-                    }
-                }
-            }
-        }
-        k0 += nbuf;
-        nbuf = 0;
-        DEGK_UNROLL for (int s = 0; s < W; ++s) srow[s] = wu + (size_t)(lane + 32 * s) * S;
-        __syncwarp();
-    };
+    if constexpr (STAGED) stage_row(ua, t0);                      // row 0 = prob.u0
 
     typename MethodV::Keep K;
     MethodV::init(K, ua, p, V(t0));
@@ -168,13 +243,8 @@ DEGK_DEV void ode_solve_lockstep_run(const KArgs& a, unsigned char* smem_raw) {
         else MethodV::template attempt<false>(K, uin, p, V(tprev), dtv, uout, err);
         ++nsteps;
         if constexpr (STAGED) {                                   // integrator_utils.jl:28-33, staged
-            DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                DEGK_UNROLL for (int c = 0; c < N; ++c) srow[s][c] = PO::get(uout[c], s);
-                srow[s] += N;
-            }
-            if (lane == 0) wt[nbuf] = t;
-            ++nbuf;
-            if (--room == 0) { flush(); room = R; }
+            stage_row(uout, t);
+            --room;
         } else {
             const bool in_range = step_idx < a.n_rows;            // rows past `len` are dropped
             DEGK_UNROLL for (int s = 0; s < W; ++s) {
@@ -196,14 +266,17 @@ DEGK_DEV void ode_solve_lockstep_run(const KArgs& a, unsigned char* smem_raw) {
     if (t < tf) {
         for (;;) {
             last_in_a = true;
-            if (!step(ua, ub)) break;
-            last_in_a = false;
-            if (!step(ub, ua)) break;
+            bool more = step(ua, ub);
+            if (more) { last_in_a = false; more = step(ub, ua); }
+            if (!more) break;
+            if constexpr (STAGED) {                               // one flush site per two steps: 8 or 9 new rows + <= 7 left over
+                if (room <= 0) { flush(false); room += PERIOD; }
+            }
         }
     } else {
         DEGK_UNROLL for (int c = 0; c < N; ++c) ub[c] = ua[c];    // no step: u = u0
     }
-    if (STAGED && nbuf > 0) flush();
+    if constexpr (STAGED) flush(true);
 
     // final state and the step it came from
     V u[N], uprev[N];

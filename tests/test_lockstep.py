@@ -65,6 +65,38 @@ def test_strict_steppers_and_overshoot_row(dg, oracle, alg, tspan, dt):
     same(g, v1, f"{alg} lock-step vs one thread per trajectory")
 
 
+@pytest.mark.parametrize("tspan,dt", [([0, 0.3], 0.1), ([0, 0.75], 0.1), ([0, 1.65], 0.1), ([0, 3.2], 0.1), ([0, 4.05], 0.05)])
+def test_short_runs_and_buffer_boundaries(dg, oracle, tspan, dt):
+    """fewer rows than one flush period, exactly one period, one more, ... : first / last ragged pieces of a trajectory"""
+    p = lorenz_sweep(200, seed=8)
+    for fp_alg in ("tsit5", "vern7"):
+        g = solve(dg, fp_alg, p, tspan, dt, engine="lockstep")
+        r = oracle.solve("lorenz", fp_alg, U0_LORENZ, p, tspan, dt=dt, length=g["us"].shape[1])
+        same(g, r, f"{fp_alg} {tspan}")
+    a = solve(dg, "tsit5", p, tspan, dt, engine="lockstep", fp_mode="fast")
+    b = solve(dg, "tsit5", p, tspan, dt, engine="lockstep", fp_mode="fast", layout="soa")
+    assert np.array_equal(a["us"], b["us"].transpose(2, 0, 1)) and np.array_equal(a["ts"], b["ts"].T)
+
+
+def test_four_component_state_without_parameters(dg):
+    """Henon-Heiles (n = 4, no parameters): other buffer strides and sector phases"""
+    from cases import henon_heiles_u0
+    u0 = henon_heiles_u0(333, seed=5).astype(f32)
+    import torch
+    prob = dg.ODEProblem(dg.models.henon_heiles, u0[0], (0.0, 7.0), None)
+    probs = dg.ProblemBatch.from_arrays(prob, u0=u0, device="cuda:0")
+    out = {}
+    for engine in ("lockstep", "v1"):
+        for fp in ("strict", "fast"):
+            ts, us, st = dg.vectorized_solve(probs, prob, dg.GPUVern7(), dt=f32(0.05), fp_mode=fp, stats=True, engine=engine)
+            torch.cuda.synchronize()
+            out[engine, fp] = (ts.cpu().numpy(), us.cpu().numpy(), st["naccept"].cpu().numpy())
+    for k in range(3):
+        assert np.array_equal(out["lockstep", "strict"][k], out["v1", "strict"][k])
+    assert np.array_equal(out["lockstep", "fast"][0], out["v1", "fast"][0])
+    assert np.abs(out["lockstep", "fast"][1] - out["v1", "fast"][1]).max() < 1e-3
+
+
 def test_float64_strict_equals_the_per_thread_kernel(dg):
     p = lorenz_sweep(500, seed=3).astype(f64)
     for alg in ("tsit5", "vern9"):
