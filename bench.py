@@ -161,6 +161,33 @@ def run_c5(dg, torch, dev, world, traj_total, steps, warmup, fp):
                     "d2h_bytes_per_step": 13 * 8, "note": "host clock around dg.solve(...): problem upload, solve, all-reduce, moments to host"}}
 
 
+def run_c1(dg, torch, dev, traj=1_000_000, launches=20):
+    """BASELINE config 1 (Lorenz GPUTsit5, fixed dt = 0.1, every-step saves, Float32) at `traj` trajectories per GPU in the
+    reference's array layout: vectorized_solve -> the lock-step kernel.  `launches` calls are enqueued back to back between
+    two CUDA events (outputs 1.6 GB per call: far beyond the L2); both fp modes."""
+    f32 = np.float32
+    g = torch.Generator(device=dev).manual_seed(11)
+    p = torch.rand((traj, 3), generator=g, device=dev) * torch.tensor(P0, device=dev)
+    prob = dg.ODEProblem(dg.models.lorenz, U0, (0.0, 10.0), P0)
+    probs = dg.ProblemBatch.from_arrays(prob, p=p, device=dev)
+    out = {"workload": f"C1: Lorenz GPUTsit5 fixed dt=0.1, tspan 0-10, every-step saves (101 rows), f32, {traj} trajectories/GPU, reference layout",
+           "unit": "trajectory-steps/s", "launches": launches}
+    for fp in ("strict", "fast"):
+        fn = lambda: dg.vectorized_solve(probs, prob, dg.GPUTsit5(), dt=f32(0.1), fp_mode=fp)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(launches):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / launches
+        out[fp] = {"value": traj * 100 / (ms * 1e-3), "ms_per_launch": ms}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,6 +359,13 @@ def main():
         c5 = run_c5(dg, torch, dev, world, args.c5_traj, 3, 2, args.fp)
     except Exception as ex:       # the headline line survives a failure here
         c5 = {"error": repr(ex)}
+    # ---- BASELINE config 1 at 10^6 trajectories per GPU (the lock-step fixed-dt kernel) ----
+    c1 = None
+    try:
+        torch.cuda.empty_cache()
+        c1 = run_c1(dg, torch, dev)
+    except Exception as ex:
+        c1 = {"error": repr(ex)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -399,7 +433,7 @@ def main():
                    "regs_per_thread": info.regs_adaptive2, "blocks_per_sm": info.max_blocks_per_sm2,
                    "trajectories_per_thread": info.slots_per_thread2, "threads_per_block": 128},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "strict_fp": other,
-        "roofline": roofline, "cpu_baseline": cpu, "c5": c5,
+        "roofline": roofline, "cpu_baseline": cpu, "c5": c5, "c1": c1,
     }))
 
 

@@ -47,7 +47,7 @@ Base.@kwdef struct SolveArgs
     out_layout::Int32 = 0; schedule::Int32 = 2
     retcode::CuPtr{Int32} = CU_NULL; naccept::CuPtr{Int32} = CU_NULL; nreject::CuPtr{Int32} = CU_NULL
     seed::UInt64 = 0; reduce::CuPtr{Float64} = CU_NULL; totals::CuPtr{UInt64} = CU_NULL
-    max_iters::Int64 = 0; engine::Int32 = 0; dae_init::Int32 = 0
+    max_iters::Int64 = 0; engine::Int32 = 0; dae_init::Int32 = 0   # engine: degk_engine (0 auto, 1 per-thread kernels, 2 lock-step fixed dt)
     tstops::CuPtr{Cvoid} = CU_NULL; n_tstops::Int32 = 0; reserved2::Int32 = 0
     nsaved::CuPtr{Int32} = CU_NULL
     saveat_stride::Int64 = 0                                  # per-problem saveat grids (kernels.jl:15-17): elements between two grids
