@@ -519,7 +519,26 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
         // ---------------- error norm and step-size control ----------------
         bool rej[W];
         T hf_[W], lqa_[W], rem_[W], tsum_[W];
-        if constexpr (FAST) {
+        if constexpr (FAST && sizeof(T) == 8) {
+            // Float64 fast build: the error norm decides accept / reject and feeds the step-size factor -- a few digits
+            // are enough, so the scaled errors are formed in Float32 with the MUFU reciprocal / log2 / exp2 (the
+            // Float64 division, log2 and exp2 were ~190 of the ~650 instructions of a Vern9 attempt)
+            static_assert(W == 1, "Float64 runs one trajectory per thread");
+            float accf = 0.f;
+            DEGK_UNROLL for (int c = 0; c < N; ++c) {
+                const float sc = (float)fma_(vmaxabs(u[c], unew[c]), reltol, abstol);
+                const float v = (float)err[c] * rcp_(sc);
+                accf = fmaf(v, v, accf);
+            }
+            const float Lf = log2_(accf);                            // log2(N * EEst^2)
+            rej[0] = accf > (float)N;                                // EEst > 1
+            const float lqe = rej[0] ? (float)lqZero : (float)lq[0];
+            const float ex = vclamp(fmaf(-(float)b1h, Lf, fmaf((float)b2h, lqe, (float)k0)), (float)exLo, (float)exHi);
+            hf_[0] = h[0] * (T)exp2_(ex);                            // dt * fac
+            tsum_[0] = t[0] + h[0];
+            rem_[0] = tf[0] - tsum_[0];                              // what is left after this step (exact when small)
+            lqa_[0] = (T)fmaxf(Lf, (float)lqInit);
+        } else if constexpr (FAST) {
             // tmp ./ (abstol .+ max.(abs.(uprev), abs.(u)) * reltol), sum of squares (ODE_DEFAULT_NORM), packed
             V accn;
             DEGK_UNROLL for (int c = 0; c < N; ++c) {

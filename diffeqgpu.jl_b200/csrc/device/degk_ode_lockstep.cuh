@@ -87,6 +87,33 @@ __device__ __noinline__ void lockstep_flush_array(T* base, const T* buf0, int st
     const int rw = (int)(row_words & (SW - 1));
     int phi = (int)((((unsigned long long)base / sizeof(T)) + (unsigned long long)((warp_first + sub) * row_words)) & (unsigned long long)(SW - 1));
     const T* bj = buf0 + (size_t)sub * stride;
+    if (!final && kpr >= SW) {
+        // steady state: both ends of the window are sector boundaries (lockstep_window reduces to two roundings)
+        for (int j = sub; j < nstrips; j += PER_IT, tb += PER_IT * row_words, bj += PER_IT * stride, phi = (phi + PER_IT * rw) & (SW - 1)) {
+            const int F = ((wpr + phi) & ~(SW - 1)) - phi, E = ((whi + phi) & ~(SW - 1)) - phi;
+            const int nq = (E - F) / QW;
+            T* dst = tb + F + q0 * QW;
+            _Pragma("unroll 1")
+            for (int q = q0; q < nq; q += LPS, dst += LPS * QW) {
+                uint4 pk;
+                if constexpr (LINEAR) {
+                    pk = *reinterpret_cast<const uint4*>(bj + q * QW);
+                } else {
+                    const int r = F + q * QW;
+                    T v[QW];
+                    DEGK_UNROLL for (int i = 0; i < QW; ++i) v[i] = bj[(r + i) & (RING - 1)];
+                    if constexpr (sizeof(T) == 4) {
+                        pk = make_uint4(__float_as_uint((float)v[0]), __float_as_uint((float)v[1]), __float_as_uint((float)v[QW - 2]), __float_as_uint((float)v[QW - 1]));
+                    } else {
+                        const unsigned long long l0 = (unsigned long long)__double_as_longlong((double)v[0]), l1 = (unsigned long long)__double_as_longlong((double)v[QW - 1]);
+                        pk = make_uint4((unsigned)l0, (unsigned)(l0 >> 32), (unsigned)l1, (unsigned)(l1 >> 32));
+                    }
+                }
+                *reinterpret_cast<uint4*>(dst) = pk;
+            }
+        }
+        return;
+    }
     for (int j = sub; j < nstrips; j += PER_IT, tb += PER_IT * row_words, bj += PER_IT * stride, phi = (phi + PER_IT * rw) & (SW - 1)) {
         int F, Fa, Ea, E;
         lockstep_window<SW>(phi, wpr, whi, final, F, Fa, Ea, E);
@@ -178,7 +205,8 @@ DEGK_DEV void ode_solve_lockstep_run(const KArgs& a, unsigned char* smem_raw) {
     auto flush = [&](bool final) {
         __syncwarp();
         lockstep_flush_array<T, N, 8, true, RING>((T*)a.us, wu, S, warp_first, nstrips, a.n_rows, k_prev, k_hi, final);
-        if (a.ts != nullptr) lockstep_flush_array<T, 1, 4, false, RING>((T*)a.ts, wt, 0, warp_first, nstrips, a.n_rows, k_prev, k_hi, final);
+        // (the save times of a steady-state flush are PERIOD rows = PERIOD / 4 sixteen-byte stores per trajectory)
+        if (a.ts != nullptr) lockstep_flush_array<T, 1, (PERIOD * (int)sizeof(T) / 16 >= 8 ? 8 : (PERIOD * (int)sizeof(T) / 16 >= 4 ? 4 : 2)), false, RING>((T*)a.ts, wt, 0, warp_first, nstrips, a.n_rows, k_prev, k_hi, final);
         __syncwarp();
         if (!final) {
             // every lane moves what its trajectories keep (the words behind their last sector boundary, fewer than
@@ -186,7 +214,12 @@ DEGK_DEV void ode_solve_lockstep_run(const KArgs& a, unsigned char* smem_raw) {
             const i64 khi = k_hi < a.n_rows ? k_hi : a.n_rows, kpr = k_prev < khi ? k_prev : khi;
             DEGK_UNROLL for (int s = 0; s < W; ++s) {
                 int F, Fa, Ea, E;
-                lockstep_window<SW>(phis[s], (int)kpr * N, (int)khi * N, false, F, Fa, Ea, E);
+                if (kpr >= SW) {                                  // steady state: two roundings (see lockstep_flush_array)
+                    F = (((int)kpr * N + phis[s]) & ~(SW - 1)) - phis[s];
+                    E = (((int)khi * N + phis[s]) & ~(SW - 1)) - phis[s];
+                } else {
+                    lockstep_window<SW>(phis[s], (int)kpr * N, (int)khi * N, false, F, Fa, Ea, E);
+                }
                 T* b = wu + (size_t)(lane + 32 * s) * S;
                 const int keep = (int)khi * N - E, off = E - F;
                 if (off > 0) {
