@@ -29,11 +29,13 @@ template <class T, int N>
 struct LinSolve {
     T lu[N][N];          // n>=4: L (unit, below diag) and U;  n<=3: cofactor matrix
     T dinv[N];           // n>=4: 1/U_jj ; n<=3: dinv[0] = det (strict) or 1/det (fast)
+    T ndinv;             // n<=3: -dinv[0] (solve_neg)
     int piv[N];          // n>=4: row interchanged with row k at elimination step k
 
     DEGK_DEV bool factor(const T (&A)[N][N]) {
         if constexpr (N == 1) {
             dinv[0] = (T)1 / A[0][0];
+            ndinv = -dinv[0];
             return true;
         } else if constexpr (N == 2) {
             const T d = A[0][0] * A[1][1] - A[0][1] * A[1][0];
@@ -42,6 +44,7 @@ struct LinSolve {
 #else
             dinv[0] = (T)1 / d;
 #endif
+            ndinv = -dinv[0];
             lu[0][0] = A[1][1]; lu[0][1] = A[0][1]; lu[1][0] = A[1][0]; lu[1][1] = A[0][0];
             return true;
         } else if constexpr (N == 3) {
@@ -59,6 +62,7 @@ struct LinSolve {
 #else
             dinv[0] = (T)1 / d;
 #endif
+            ndinv = -dinv[0];
             return true;
         } else {
             DEGK_UNROLL_LU for (int i = 0; i < N; ++i)
@@ -90,6 +94,38 @@ struct LinSolve {
                 dinv[j] = (T)1 / lu[j][j];
             }
             return ok;
+        }
+    }
+
+    // x = A \ (-b), bit for bit what solve() returns for the negated right-hand side (products, sums, quotients are
+    // sign-symmetric under round-to-nearest), without negating b: for the closed forms the sign rides on the
+    // determinant factor -- one negation per solve instead of one per component, and for packed pairs (whose negation
+    // is two integer XORs the FMA pipe cannot fold) none at all in the stage arithmetic.
+    DEGK_DEV void solve_neg(const T (&b)[N], T (&x)[N]) const {
+        if constexpr (N == 1) {
+            x[0] = ndinv * b[0];
+        } else if constexpr (N == 2) {
+            const T nd = ndinv;
+#if DEGK_STRICT
+            x[0] = (lu[0][0] * b[0] - lu[0][1] * b[1]) / nd;
+            x[1] = (lu[1][1] * b[1] - lu[1][0] * b[0]) / nd;
+#else
+            x[0] = (lu[0][0] * b[0] - lu[0][1] * b[1]) * nd;
+            x[1] = (lu[1][1] * b[1] - lu[1][0] * b[0]) * nd;
+#endif
+        } else if constexpr (N == 3) {
+            const T nd = ndinv;
+            DEGK_UNROLL for (int i = 0; i < 3; ++i) {
+                const T s = (lu[i][0] * b[0] + lu[i][1] * b[1]) + lu[i][2] * b[2];
+#if DEGK_STRICT
+                x[i] = s / nd;
+#else
+                x[i] = s * nd;
+#endif
+            }
+        } else {
+            solve(b, x);
+            DEGK_UNROLL_LU for (int i = 0; i < N; ++i) x[i] = -x[i];
         }
     }
 
@@ -160,6 +196,7 @@ struct Rosenbrock23 {
         eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
         eval_tgrad<T, Model>(dT, uprev, p, t);
         constexpr bool MASS = has_mass_of<Model>::value;     // W = mass_matrix - gamma*J (:45, :120)
+        const T ngam = -gam;
         T Mm[MASS ? N : 1][MASS ? N : 1];
         if constexpr (MASS) {
             Model::template mass<T>(Mm);
@@ -168,7 +205,7 @@ struct Rosenbrock23 {
         } else {
             DEGK_UNROLL for (int i = 0; i < N; ++i)
                 DEGK_UNROLL for (int j = 0; j < N; ++j) {
-                    const T v = -(gam * J[i][j]);
+                    const T v = ngam * J[i][j];              // -(gam * J): the sign rides on the scalar
                     W[i][j] = (i == j) ? v + (T)1 : v;
                 }
         }
@@ -274,24 +311,24 @@ struct Rodas {
         Model::template f<T>(du, uprev, p, t);
         // Step 1
         { const T dtd1 = h * RC(d1);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + dtd1 * dT[c]); }
-        F.solve(lt, k[0]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + dtd1 * dT[c]; }
+        F.solve_neg(lt, k[0]);
         DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uprev[c] + RC(a21) * k[0][c];
         Model::template f<T>(du, uu, p, t + RC(c2) * h);
         // Step 2
         { const T dtd2 = h * RC(d2), C21 = RC(C21) / h;
           DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = C21 * k[0][c];
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd2 * dT[c]) + cs[c]); }
-        F.solve(lt, k[1]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd2 * dT[c]) + cs[c]; }
+        F.solve_neg(lt, k[1]);
         DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = (uprev[c] + RC(a31) * k[0][c]) + RC(a32) * k[1][c];
         Model::template f<T>(du, uu, p, t + RC(c3) * h);
         // Step 3
         { const T dtd3 = h * RC(d3), C31 = RC(C31) / h, C32 = RC(C32) / h;
           DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (C31 * k[0][c] + C32 * k[1][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd3 * dT[c]) + cs[c]); }
-        F.solve(lt, k[2]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd3 * dT[c]) + cs[c]; }
+        F.solve_neg(lt, k[2]);
         DEGK_UNROLL for (int c = 0; c < N; ++c)
             uu[c] = ((uprev[c] + RC(a41) * k[0][c]) + RC(a42) * k[1][c]) + RC(a43) * k[2][c];
         Model::template f<T>(du, uu, p, t + RC(c4) * h);
@@ -299,8 +336,8 @@ struct Rodas {
         { const T dtd4 = h * RC(d4), C41 = RC(C41) / h, C42 = RC(C42) / h, C43 = RC(C43) / h;
           DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((C41 * k[0][c] + C42 * k[1][c]) + C43 * k[2][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd4 * dT[c]) + cs[c]); }
-        F.solve(lt, k[3]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd4 * dT[c]) + cs[c]; }
+        F.solve_neg(lt, k[3]);
         DEGK_UNROLL for (int c = 0; c < N; ++c)
             uu[c] = (((uprev[c] + RC(a51) * k[0][c]) + RC(a52) * k[1][c]) + RC(a53) * k[2][c]) + RC(a54) * k[3][c];
         const T C51 = RC(C51) / h, C52 = RC(C52) / h, C53 = RC(C53) / h, C54 = RC(C54) / h;
@@ -310,8 +347,8 @@ struct Rodas {
             { const T dtd5 = h * R5C(d5);
               DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -((du[c] + dtd5 * dT[c]) + cs[c]); }
-            F.solve(lt, k[4]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd5 * dT[c]) + cs[c]; }
+            F.solve_neg(lt, k[4]);
             DEGK_UNROLL for (int c = 0; c < N; ++c)
                 uu[c] = ((((uprev[c] + R5C(a61) * k[0][c]) + R5C(a62) * k[1][c]) + R5C(a63) * k[2][c]) +
                          R5C(a64) * k[3][c]) + R5C(a65) * k[4][c];
@@ -320,8 +357,8 @@ struct Rodas {
             { const T C61 = R5C(C61) / h, C62 = R5C(C62) / h, C63 = R5C(C63) / h, C64 = R5C(C64) / h, C65 = R5C(C65) / h;
               DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((C61 * k[0][c] + C62 * k[1][c]) + C63 * k[2][c]) + C64 * k[3][c]) + C65 * k[4][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
-            F.solve(lt, k[5]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
+            F.solve_neg(lt, k[5]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[5][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 7
@@ -330,8 +367,8 @@ struct Rodas {
               DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((((C71 * k[0][c] + C72 * k[1][c]) + C73 * k[2][c]) + C74 * k[3][c]) +
                                       C75 * k[4][c]) + C76 * k[5][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
-            F.solve(lt, k[NS > 6 ? 6 : 0]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
+            F.solve_neg(lt, k[NS > 6 ? 6 : 0]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[NS > 6 ? 6 : 0][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 8
@@ -340,24 +377,24 @@ struct Rodas {
               DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((((C81 * k[0][c] + C82 * k[1][c]) + C83 * k[2][c]) + C84 * k[3][c]) +
                                        C85 * k[4][c]) + C86 * k[5][c]) + C87 * k[NS > 6 ? 6 : 0][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
-            F.solve(lt, k[NS - 1]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
+            F.solve_neg(lt, k[NS - 1]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uu[c] + k[NS - 1][c];
         } else {
             Model::template f<T>(du, uu, p, t + h);
             // Step 5: summands in the order k2,k4,k1,k3 (gpu_rodas4_perform_step.jl:213)
             DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]);
-            F.solve(lt, k[4]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c];
+            F.solve_neg(lt, k[4]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[4][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 6: summands in the order k1,k2,k5,k4,k3 (:219)
             { const T C61 = R4C(C61) / h, C62 = R4C(C62) / h, C63 = R4C(C63) / h, C64 = R4C(C64) / h, C65 = R4C(C65) / h;
               DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((C61 * k[0][c] + C62 * k[1][c]) + C65 * k[4][c]) + C64 * k[3][c]) + C63 * k[2][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = -(du[c] + cs[c]); }
-            F.solve(lt, k[5]);
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
+            F.solve_neg(lt, k[5]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uu[c] + k[5][c];
         }
         if (WANT_ERR) {
