@@ -434,7 +434,7 @@ def main():
                    "trajectories_per_thread": info.slots_per_thread2, "threads_per_block": 128},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "strict_fp": other,
         "roofline": roofline, "cpu_baseline": cpu, "c5": c5, "c1": c1,
-    }))
+    }), flush=True)
 
 
 if __name__ == "__main__":
