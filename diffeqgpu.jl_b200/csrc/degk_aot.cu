@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(DEGK_BLOCK2, (lockstep_minblocks<T>())) k_ode_
     ode_solve_lockstep_body<T, Model, Method, W>(a, degk_smem);
 }
 template <int FPMODE, class T, class Model, int ALG>
-__global__ void __launch_bounds__(DEGK_BLOCK) k_sde_solve(const KArgs a) {
+__global__ void __launch_bounds__(DEGK_BLOCK, DEGK_SDE_MINBLOCKS) k_sde_solve(const KArgs a) {
     sde_solve_body<T, Model, ALG>(a);
 }
 

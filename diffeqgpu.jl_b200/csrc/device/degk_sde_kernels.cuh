@@ -13,6 +13,13 @@
 #pragma once
 #include "degk_common.cuh"
 
+#ifndef DEGK_SDE_PAIR
+#define DEGK_SDE_PAIR 1      // end-point runs: two steps per loop trip (see sde_solve_body)
+#endif
+#ifndef DEGK_SDE_MINBLOCKS
+#define DEGK_SDE_MINBLOCKS 1
+#endif
+
 namespace degk {
 
 enum { ALG_EM = 0, ALG_SIEA = 1 };
@@ -130,10 +137,8 @@ DEGK_DEV void sde_solve_body(const KArgs& a) {
     // n = floor(Int, abs(tf - t0) / abs(dt)) + 1   (gpu_em_perform_step.jl:44)
     const i64 nst = (i64)floor((double)(abs_(tf - t0) / abs_(dt))) + 1;
     // one step: u <- stepper(uprev = u), t <- t + dt
-    auto advance = [&](i64 j) {
+    auto advance_z = [&](const T (&z)[MM]) {
         DEGK_UNROLL for (int c = 0; c < N; ++c) uprev[c] = u[c];
-        T z[MM];
-        normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 2), z);
         if constexpr (ALG == ALG_EM) {
             T f[N];
             Model::template f<T>(f, uprev, p, t);
@@ -183,10 +188,26 @@ DEGK_DEV void sde_solve_body(const KArgs& a) {
         }
         t = t + dt;
     };
+    auto advance = [&](i64 j) {
+        T z[MM];
+        normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 2), z);
+        advance_z(z);
+    };
     if (!has_saveat && !a.save_everystep) {
         // endpoints only (ensemble moments, BASELINE config 5): nothing to test or store per step -- the general loop
-        // below spends ~25 of its 129 instructions per step on the save options
-        for (i64 j = 2; j <= nst; ++j) advance(j);
+        // below spends ~25 of its 129 instructions per step on the save options.  Two steps per trip: the normals do
+        // not depend on the state, so both Philox chains (ten serial rounds each) are in flight together.
+        i64 j = 2;
+#if DEGK_SDE_PAIR
+        for (; j + 1 <= nst; j += 2) {
+            T z0[MM], z1[MM];
+            normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 2), z0);
+            normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 1), z1);
+            advance_z(z0);
+            advance_z(z1);
+        }
+#endif
+        for (; j <= nst; ++j) advance(j);
     }
     for (i64 j = 2; j <= nst && (has_saveat || a.save_everystep); ++j) {
         advance(j);
