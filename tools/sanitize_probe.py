@@ -28,6 +28,20 @@ for fp in ("fast", "strict"):
 big = dg.ProblemBatch.from_arrays(prob, p=lorenz_sweep(148 * 256 * 3 + 77, seed=2), device="cuda:0")
 prob_s = dg.ODEProblem(dg.models.lorenz, np.array([1, 0, 0], f32), (0.0, 0.5), np.array([10, 28, 8 / 3], f32))
 dg.vectorized_solve(big, prob_s, dg.GPUTsit5(), dt=f32(0.01))
+# lock-step fixed-dt kernel: both layouts, ragged sizes, short and long runs, Float64, end-point SDE loop
+for fp in ("fast", "strict"):
+    for n, tspan, dt in ((1, (0.0, 0.3), 0.1), (97, (0.0, 1.65), 0.1), (4099, (0.0, 10.0), 0.1), (641, (0.5, 3.0), 0.07)):
+        pr = dg.ODEProblem(dg.models.lorenz, np.array([1, 0, 0], f32), tspan, np.array([10, 28, 8 / 3], f32))
+        pb = dg.ProblemBatch.from_arrays(pr, p=lorenz_sweep(n, seed=3), device="cuda:0")
+        for layout in ("ref", "soa"):
+            dg.vectorized_solve(pb, pr, dg.GPUTsit5(), dt=f32(dt), fp_mode=fp, layout=layout, engine="lockstep")
+        dg.vectorized_solve(pb, pr, dg.GPUVern9(), dt=f32(dt), fp_mode=fp, engine="lockstep")
+    pr64 = dg.ODEProblem(dg.models.lorenz, np.array([1.0, 0, 0]), (0.0, 2.0), np.array([10, 28, 8 / 3]))
+    pb64 = dg.ProblemBatch.from_arrays(pr64, p=lorenz_sweep(333, seed=4).astype(np.float64), device="cuda:0")
+    dg.vectorized_solve(pb64, pr64, dg.GPUTsit5(), dt=0.05, fp_mode=fp, engine="lockstep")
+    sp = dg.SDEProblem(dg.models.lorenz_additive, np.array([1, 0, 0], f32), (0.0, 0.05), np.array([10, 28, 8 / 3], f32), seed=5)
+    dg.solve(dg.EnsembleProblem(sp, reduction=dg.EnsembleMoments()), dg.GPUEM(), dg.EnsembleGPUKernel(dev="cuda:0", fp_mode=fp),
+             trajectories=1001, dt=f32(1e-3), save_everystep=False, adaptive=False)
 cb = dg.DiscreteCallback(*callback_sources((("u_gt", 2, 30.0), ("u_scale", 2, 0.5))))
 dg.vectorized_asolve(probs, prob, dg.GPUTsit5(), dt=f32(0.1), saveat=sv, callback=cb, tstops=[1.5])
 dg.vectorized_asolve(probs, prob, dg.GPUKvaerno3(), dt=f32(0.01), save_everystep=False)
