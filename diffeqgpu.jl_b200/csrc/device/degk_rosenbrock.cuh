@@ -289,6 +289,21 @@ struct Rodas {
         T J[N][N], dT[N];
         eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
         eval_tgrad<T, Model>(dT, uprev, p, t);
+        // The stage right-hand sides hold sum_j (C_ij / dt) k_j.  Strict: dtC_ij = C_ij / dt first, then the products,
+        // as the reference writes it.  Fast: the sum with the C_ij as immediates, one multiply by 1/dt per component --
+        // seven packed multiplies fewer per attempt, and 84 FFMA2 read an immediate instead of a third register pair
+        // (2.08 instead of 3.06 issue cycles each, profiles/r2_pipe_probe2.jsonl).
+#ifndef DEGK_ROS_HINV
+#define DEGK_ROS_HINV 1
+#endif
+#if DEGK_STRICT || !DEGK_ROS_HINV
+#define CH_(v) ((v) / h)
+#define CSC_(v) (v)
+#else
+        const T hinv = (T)1 / h;
+#define CH_(v) (v)
+#define CSC_(v) (hinv * (v))
+#endif
         const T dtgamma = h * RC(gamma);
         const T invdg = (T)1 / dtgamma;
         // W = J - mass_matrix * inv(dtgamma) (gpu_rodas5P_perform_step.jl:81-82, 238-239); every
@@ -316,16 +331,16 @@ struct Rodas {
         DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uprev[c] + RC(a21) * k[0][c];
         Model::template f<T>(du, uu, p, t + RC(c2) * h);
         // Step 2
-        { const T dtd2 = h * RC(d2), C21 = RC(C21) / h;
-          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = C21 * k[0][c];
+        { const T dtd2 = h * RC(d2), C21 = CH_(RC(C21));
+          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_(C21 * k[0][c]);
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd2 * dT[c]) + cs[c]; }
         F.solve_neg(lt, k[1]);
         DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = (uprev[c] + RC(a31) * k[0][c]) + RC(a32) * k[1][c];
         Model::template f<T>(du, uu, p, t + RC(c3) * h);
         // Step 3
-        { const T dtd3 = h * RC(d3), C31 = RC(C31) / h, C32 = RC(C32) / h;
-          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (C31 * k[0][c] + C32 * k[1][c]);
+        { const T dtd3 = h * RC(d3), C31 = CH_(RC(C31)), C32 = CH_(RC(C32));
+          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_((C31 * k[0][c] + C32 * k[1][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd3 * dT[c]) + cs[c]; }
         F.solve_neg(lt, k[2]);
@@ -333,19 +348,19 @@ struct Rodas {
             uu[c] = ((uprev[c] + RC(a41) * k[0][c]) + RC(a42) * k[1][c]) + RC(a43) * k[2][c];
         Model::template f<T>(du, uu, p, t + RC(c4) * h);
         // Step 4
-        { const T dtd4 = h * RC(d4), C41 = RC(C41) / h, C42 = RC(C42) / h, C43 = RC(C43) / h;
-          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((C41 * k[0][c] + C42 * k[1][c]) + C43 * k[2][c]);
+        { const T dtd4 = h * RC(d4), C41 = CH_(RC(C41)), C42 = CH_(RC(C42)), C43 = CH_(RC(C43));
+          DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_(((C41 * k[0][c] + C42 * k[1][c]) + C43 * k[2][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd4 * dT[c]) + cs[c]; }
         F.solve_neg(lt, k[3]);
         DEGK_UNROLL for (int c = 0; c < N; ++c)
             uu[c] = (((uprev[c] + RC(a51) * k[0][c]) + RC(a52) * k[1][c]) + RC(a53) * k[2][c]) + RC(a54) * k[3][c];
-        const T C51 = RC(C51) / h, C52 = RC(C52) / h, C53 = RC(C53) / h, C54 = RC(C54) / h;
+        const T C51 = CH_(RC(C51)), C52 = CH_(RC(C52)), C53 = CH_(RC(C53)), C54 = CH_(RC(C54));
         if (R5) {
             Model::template f<T>(du, uu, p, t + R5C(c5) * h);
             // Step 5: summands in the order k2,k4,k1,k3 (gpu_rodas5P_perform_step.jl:271)
             { const T dtd5 = h * R5C(d5);
-              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]);
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_((((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd5 * dT[c]) + cs[c]; }
             F.solve_neg(lt, k[4]);
@@ -354,28 +369,28 @@ struct Rodas {
                          R5C(a64) * k[3][c]) + R5C(a65) * k[4][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 6
-            { const T C61 = R5C(C61) / h, C62 = R5C(C62) / h, C63 = R5C(C63) / h, C64 = R5C(C64) / h, C65 = R5C(C65) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((C61 * k[0][c] + C62 * k[1][c]) + C63 * k[2][c]) + C64 * k[3][c]) + C65 * k[4][c]);
+            { const T C61 = CH_(R5C(C61)), C62 = CH_(R5C(C62)), C63 = CH_(R5C(C63)), C64 = CH_(R5C(C64)), C65 = CH_(R5C(C65));
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_(((((C61 * k[0][c] + C62 * k[1][c]) + C63 * k[2][c]) + C64 * k[3][c]) + C65 * k[4][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
             F.solve_neg(lt, k[5]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[5][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 7
-            { const T C71 = R5C(C71) / h, C72 = R5C(C72) / h, C73 = R5C(C73) / h, C74 = R5C(C74) / h,
-                      C75 = R5C(C75) / h, C76 = R5C(C76) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((((C71 * k[0][c] + C72 * k[1][c]) + C73 * k[2][c]) + C74 * k[3][c]) +
-                                      C75 * k[4][c]) + C76 * k[5][c]);
+            { const T C71 = CH_(R5C(C71)), C72 = CH_(R5C(C72)), C73 = CH_(R5C(C73)), C74 = CH_(R5C(C74)),
+                      C75 = CH_(R5C(C75)), C76 = CH_(R5C(C76));
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_((((((C71 * k[0][c] + C72 * k[1][c]) + C73 * k[2][c]) + C74 * k[3][c]) +
+                                      C75 * k[4][c]) + C76 * k[5][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
             F.solve_neg(lt, k[NS > 6 ? 6 : 0]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[NS > 6 ? 6 : 0][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 8
-            { const T C81 = R5C(C81) / h, C82 = R5C(C82) / h, C83 = R5C(C83) / h, C84 = R5C(C84) / h,
-                      C85 = R5C(C85) / h, C86 = R5C(C86) / h, C87 = R5C(C87) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((((C81 * k[0][c] + C82 * k[1][c]) + C83 * k[2][c]) + C84 * k[3][c]) +
-                                       C85 * k[4][c]) + C86 * k[5][c]) + C87 * k[NS > 6 ? 6 : 0][c]);
+            { const T C81 = CH_(R5C(C81)), C82 = CH_(R5C(C82)), C83 = CH_(R5C(C83)), C84 = CH_(R5C(C84)),
+                      C85 = CH_(R5C(C85)), C86 = CH_(R5C(C86)), C87 = CH_(R5C(C87));
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_(((((((C81 * k[0][c] + C82 * k[1][c]) + C83 * k[2][c]) + C84 * k[3][c]) +
+                                       C85 * k[4][c]) + C86 * k[5][c]) + C87 * k[NS > 6 ? 6 : 0][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
             F.solve_neg(lt, k[NS - 1]);
@@ -383,20 +398,22 @@ struct Rodas {
         } else {
             Model::template f<T>(du, uu, p, t + h);
             // Step 5: summands in the order k2,k4,k1,k3 (gpu_rodas4_perform_step.jl:213)
-            DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = (((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]);
+            DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_((((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c];
             F.solve_neg(lt, k[4]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uu[c] + k[4][c];
             Model::template f<T>(du, uu, p, t + h);
             // Step 6: summands in the order k1,k2,k5,k4,k3 (:219)
-            { const T C61 = R4C(C61) / h, C62 = R4C(C62) / h, C63 = R4C(C63) / h, C64 = R4C(C64) / h, C65 = R4C(C65) / h;
-              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = ((((C61 * k[0][c] + C62 * k[1][c]) + C65 * k[4][c]) + C64 * k[3][c]) + C63 * k[2][c]);
+            { const T C61 = CH_(R4C(C61)), C62 = CH_(R4C(C62)), C63 = CH_(R4C(C63)), C64 = CH_(R4C(C64)), C65 = CH_(R4C(C65));
+              DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_(((((C61 * k[0][c] + C62 * k[1][c]) + C65 * k[4][c]) + C64 * k[3][c]) + C63 * k[2][c]));
           MASSV(cs);
           DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + cs[c]; }
             F.solve_neg(lt, k[5]);
             DEGK_UNROLL for (int c = 0; c < N; ++c) unew[c] = uu[c] + k[5][c];
         }
+#undef CH_
+#undef CSC_
         if (WANT_ERR) {
             DEGK_UNROLL for (int c = 0; c < N; ++c) err[c] = k[NS - 1][c];
         }

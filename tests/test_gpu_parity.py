@@ -299,9 +299,39 @@ def test_c4_robertson_rodas5p_full_size(dg, oracle, fp):
     else:
         assert (np.abs(g["us"][idx] - r["us"]) / np.maximum(np.abs(r["us"]), 1e-3)).max() < 10 * 1e-4
         # (about 90 accepted steps each at reltol 1e-4; the Float32 error estimate of a stiff stepper is sensitive
-        #  to the last bits, so fused arithmetic moves the count by a few steps: within 5 % on >= 99 %)
+        #  to the last bits, so fused arithmetic and the fast build's (1/h) * sum(C_ij k_j) -- instead of sum((C_ij/h) k_j)
+        #  -- move the count by a few steps: measured quantiles of |dn| are 2 / 3 / 5 / 6 (50 / 90 / 99 / 100 %), so the
+        #  band is 7 % on >= 99 %.  That this is not a loss of accuracy is test_c4_fast_accuracy_against_float64 below.)
         dn = np.abs(g["naccept"][idx].astype(int) - r["naccept"].astype(int))
-        assert (dn <= np.maximum(2, 0.05 * r["naccept"])).mean() >= 0.99, np.quantile(dn, [0.5, 0.9, 0.99, 1.0])
+        assert (dn <= np.maximum(2, 0.07 * r["naccept"])).mean() >= 0.99, np.quantile(dn, [0.5, 0.9, 0.99, 1.0])
+
+
+def test_c4_fast_accuracy_against_float64(dg):
+    """The fast Rodas5P build is judged by its error against a Float64 Rodas5P solve at reltol 1e-10, not by the strict
+    build's step counts: on 8192 Robertson problems its error quantiles must stay within 15 % of the strict build's
+    (measured: median 2.84e-5 vs 2.81e-5, 99 % 1.28e-4 vs 1.31e-4) and within 3 * reltol everywhere."""
+    import torch
+    n = 8192
+    k = rober_sweep(n)
+    sv = np.array([1.0, 10.0, 1e3, 1e5])
+
+    def run(dtype, fp, abstol, reltol):
+        prob = dg.ODEProblem(dg.models.rober, np.array([1, 0, 0], dtype), (0.0, 1e5), k[0].astype(dtype))
+        probs = dg.ProblemBatch.from_arrays(prob, p=k.astype(dtype), device="cuda:0")
+        _, us, st = dg.vectorized_asolve(probs, prob, dg.GPURodas5P(), dt=dtype(1e-4), abstol=dtype(abstol), reltol=dtype(reltol),
+                                         saveat=sv.astype(dtype), fp_mode=fp, stats=True)
+        torch.cuda.synchronize()
+        return us.cpu().numpy().astype(np.float64), st["naccept"].cpu().numpy()
+
+    truth, _ = run(np.float64, "strict", 1e-13, 1e-10)
+    err = {}
+    for fp in ("strict", "fast"):
+        u, na = run(f32, fp, 1e-8, 1e-4)
+        rel = (np.abs(u - truth) / np.maximum(np.abs(truth), 1e-3)).max(axis=(1, 2))
+        err[fp] = (np.median(rel), np.quantile(rel, 0.99), rel.max(), na.mean())
+    assert err["fast"][0] <= 1.15 * err["strict"][0] and err["fast"][1] <= 1.15 * err["strict"][1], err
+    assert err["fast"][2] < 3e-4 and err["strict"][2] < 3e-4, err
+    assert abs(err["fast"][3] - err["strict"][3]) < 0.05 * err["strict"][3], err
 
 
 # ------------------------------------------------------------------------------------------
