@@ -231,6 +231,9 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
                  d->n_state, d->n_param, m, noise, d->jac_src ? "true" : "false", has_tgrad ? "true" : "false",
                  d->jac_mode == 1 ? 1 : 2);
         src += buf;
+        // a Jacobian body without a time-gradient body declares dT == 0 (autonomous right-hand side): the fast build
+        // leaves the dT terms of the Rosenbrock stages out (degk_dual.cuh, tgrad_zero_of)
+        if (d->jac_src && !d->tgrad_src) src += "    static constexpr bool TGRAD_ZERO = true;\n";
         src += "    template <class T> static DEGK_DEV void f(T (&du)[N], const T (&u)[N], const T* p, T t) {\n";
         src += d->rhs_src;
         src += "\n    }\n";

@@ -78,6 +78,11 @@ template <class M> struct jac_mode_of<M, typename void_t_<decltype(M::JAC_MODE)>
 // have one define HAS_MASS = true and mass(Mm); everything else is the identity (UniformScaling)
 template <class M, class = void> struct has_mass_of { static constexpr bool value = false; };
 template <class M> struct has_mass_of<M, typename void_t_<decltype(M::HAS_MASS)>::type> { static constexpr bool value = M::HAS_MASS; };
+// models whose time gradient is identically zero (autonomous right-hand side with a user Jacobian) say
+// TGRAD_ZERO = true: the fast build then leaves the `dt * d_i * dT` terms of the Rosenbrock stages out (adding an exact
+// zero changes nothing but the sign of a zero); the strict build keeps every term the reference has
+template <class M, class = void> struct tgrad_zero_of { static constexpr bool value = false; };
+template <class M> struct tgrad_zero_of<M, typename void_t_<decltype(M::TGRAD_ZERO)>::type> { static constexpr bool value = M::TGRAD_ZERO && !DEGK_STRICT; };
 // StaticArrays SMatrix * SVector: row sums as a left fold of the products
 template <class T, int N>
 DEGK_DEV void mass_mul(const T (&Mm)[N][N], const T (&v)[N], T (&out)[N]) {

@@ -49,6 +49,7 @@ struct HenonHeiles {   // u = (x, y, px, py); SURVEY §8d C3(ii)
 struct Rober {
     static constexpr int N = 3, NP = 3, M = 0, NOISE = 0;
     static constexpr bool HAS_JAC = true, HAS_TGRAD = true;
+    static constexpr bool TGRAD_ZERO = true;
     template <class T> static DEGK_DEV void f(T (&du)[N], const T (&u)[N], const T* p, T t) {
         du[0] = -p[0] * u[0] + p[2] * u[1] * u[2];
         du[1] = p[0] * u[0] - p[1] * (u[1] * u[1]) - p[2] * u[1] * u[2];

@@ -25,9 +25,16 @@ namespace degk {
 // rolled loops (local memory) so that compile time stays bounded.
 #define DEGK_UNROLL_LU _Pragma("unroll (N <= 8 ? N : 1)")
 
-template <class T, int N>
+// NEGINV (fast build, n = 2 or 3 only; ignored otherwise): factor() stores -inverse(A) = cofactors * (-1 / det), so
+// that each solve_neg() is the bare matrix-vector product -- for a stepper that solves 6-8 times per factorisation
+// (Rodas4 / Rodas5P) this trades N*N multiplies per factorisation for N per solve.
+#ifndef DEGK_ROS_NEGINV
+#define DEGK_ROS_NEGINV 1
+#endif
+template <class T, int N, bool NEGINV_ = false>
 struct LinSolve {
-    T lu[N][N];          // n>=4: L (unit, below diag) and U;  n<=3: cofactor matrix
+    static constexpr bool NEGINV = NEGINV_ && !DEGK_STRICT && DEGK_ROS_NEGINV && (N == 2 || N == 3);
+    T lu[N][N];          // n>=4: L (unit, below diag) and U;  n<=3: cofactor matrix (NEGINV: -inverse)
     T dinv[N];           // n>=4: 1/U_jj ; n<=3: dinv[0] = det (strict) or 1/det (fast)
     T ndinv;             // n<=3: -dinv[0] (solve_neg)
     int piv[N];          // n>=4: row interchanged with row k at elimination step k
@@ -46,6 +53,10 @@ struct LinSolve {
 #endif
             ndinv = -dinv[0];
             lu[0][0] = A[1][1]; lu[0][1] = A[0][1]; lu[1][0] = A[1][0]; lu[1][1] = A[0][0];
+            if constexpr (NEGINV) {
+                const T nd = (T)-1 / d;
+                lu[0][0] = lu[0][0] * nd; lu[0][1] = lu[0][1] * nd; lu[1][0] = lu[1][0] * nd; lu[1][1] = lu[1][1] * nd;
+            }
             return true;
         } else if constexpr (N == 3) {
             const T a11 = A[0][0], a12 = A[0][1], a13 = A[0][2];
@@ -63,6 +74,11 @@ struct LinSolve {
             dinv[0] = (T)1 / d;
 #endif
             ndinv = -dinv[0];
+            if constexpr (NEGINV) {
+                const T nd = (T)-1 / d;
+                DEGK_UNROLL for (int i = 0; i < 3; ++i)
+                    DEGK_UNROLL for (int j = 0; j < 3; ++j) lu[i][j] = lu[i][j] * nd;
+            }
             return true;
         } else {
             DEGK_UNROLL_LU for (int i = 0; i < N; ++i)
@@ -102,7 +118,12 @@ struct LinSolve {
     // determinant factor -- one negation per solve instead of one per component, and for packed pairs (whose negation
     // is two integer XORs the FMA pipe cannot fold) none at all in the stage arithmetic.
     DEGK_DEV void solve_neg(const T (&b)[N], T (&x)[N]) const {
-        if constexpr (N == 1) {
+        if constexpr (NEGINV && N == 2) {
+            x[0] = lu[0][0] * b[0] - lu[0][1] * b[1];
+            x[1] = lu[1][1] * b[1] - lu[1][0] * b[0];
+        } else if constexpr (NEGINV && N == 3) {
+            DEGK_UNROLL for (int i = 0; i < 3; ++i) x[i] = (lu[i][0] * b[0] + lu[i][1] * b[1]) + lu[i][2] * b[2];
+        } else if constexpr (N == 1) {
             x[0] = ndinv * b[0];
         } else if constexpr (N == 2) {
             const T nd = ndinv;
@@ -130,6 +151,7 @@ struct LinSolve {
     }
 
     DEGK_DEV void solve(const T (&b)[N], T (&x)[N]) const {
+        static_assert(!NEGINV, "a NEGINV factorisation only serves solve_neg()");
         if constexpr (N == 1) {
             x[0] = dinv[0] * b[0];
         } else if constexpr (N == 2) {
@@ -192,9 +214,10 @@ struct Rosenbrock23 {
         const T d = (T)1 / (two + sqrt_(two));            // stiff/types.jl:47-48
         const T gam = h * d;
         const T dto2 = h / (T)2, dto6 = h / (T)6;
+        constexpr bool TG = !tgrad_zero_of<Model>::value;    // false: dT == 0 by declaration, its terms are left out
         T J[N][N], W[N][N], dT[N];
         eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
-        eval_tgrad<T, Model>(dT, uprev, p, t);
+        if constexpr (TG) eval_tgrad<T, Model>(dT, uprev, p, t);
         constexpr bool MASS = has_mass_of<Model>::value;     // W = mass_matrix - gamma*J (:45, :120)
         const T ngam = -gam;
         T Mm[MASS ? N : 1][MASS ? N : 1];
@@ -213,7 +236,7 @@ struct Rosenbrock23 {
         if (!F.factor(W)) return false;
         T F0[N], F1[N], rhs[N], tmp[N];
         Model::template f<T>(F0, uprev, p, t);
-        DEGK_UNROLL for (int c = 0; c < N; ++c) rhs[c] = F0[c] + gam * dT[c];
+        DEGK_UNROLL for (int c = 0; c < N; ++c) rhs[c] = TG ? F0[c] + gam * dT[c] : F0[c];
         F.solve(rhs, K.k1);
         DEGK_UNROLL for (int c = 0; c < N; ++c) tmp[c] = uprev[c] + dto2 * K.k1[c];
         Model::template f<T>(F1, tmp, p, t + dto2);
@@ -237,10 +260,10 @@ struct Rosenbrock23 {
                 DEGK_UNROLL for (int c = 0; c < N; ++c) v[c] = e32 * K.k2[c] + two * K.k1[c];
                 mass_mul<T, N>(Mm, v, mv);
                 DEGK_UNROLL for (int c = 0; c < N; ++c)
-                    rhs[c] = (((F2[c] - mv[c]) + e32 * F1[c]) + two * F0[c]) + h * dT[c];
+                    { const T r_ = ((F2[c] - mv[c]) + e32 * F1[c]) + two * F0[c]; rhs[c] = TG ? r_ + h * dT[c] : r_; }
             } else {
                 DEGK_UNROLL for (int c = 0; c < N; ++c)
-                    rhs[c] = ((F2[c] - e32 * (K.k2[c] - F1[c])) - two * (K.k1[c] - F0[c])) + h * dT[c];
+                    { const T r_ = (F2[c] - e32 * (K.k2[c] - F1[c])) - two * (K.k1[c] - F0[c]); rhs[c] = TG ? r_ + h * dT[c] : r_; }
             }
             F.solve(rhs, k3);
             DEGK_UNROLL for (int c = 0; c < N; ++c) err[c] = dto6 * ((K.k1[c] - two * K.k2[c]) + k3[c]);
@@ -286,9 +309,11 @@ struct Rodas {
     template <bool WANT_ERR>
     static DEGK_DEV bool attempt(Keep& K, const T (&uprev)[N], const T* p, T t, T h,
                                  T (&unew)[N], T (&err)[N]) {
-        T J[N][N], dT[N];
+        constexpr bool TG = !tgrad_zero_of<Model>::value;    // false: dT == 0 by declaration, its terms are left out
+        T J[N][N], dT[TG ? N : 1];
         eval_jac<T, Model>(J, uprev, p, t);      // analytic, ForwardDiff-style duals or finite differences
-        eval_tgrad<T, Model>(dT, uprev, p, t);
+        if constexpr (TG) eval_tgrad<T, Model>(dT, uprev, p, t);
+#define DTD_(x, dtd, c) (TG ? (x) + (dtd) * dT[TG ? c : 0] : (x))
         // The stage right-hand sides hold sum_j (C_ij / dt) k_j.  Strict: dtC_ij = C_ij / dt first, then the products,
         // as the reference writes it.  Fast: the sum with the C_ij as immediates, one multiply by 1/dt per component --
         // seven packed multiplies fewer per attempt, and 84 FFMA2 read an immediate instead of a third register pair
@@ -304,8 +329,12 @@ struct Rodas {
 #define CH_(v) (v)
 #define CSC_(v) (hinv * (v))
 #endif
+#if DEGK_STRICT || !DEGK_ROS_HINV
         const T dtgamma = h * RC(gamma);
         const T invdg = (T)1 / dtgamma;
+#else
+        const T invdg = hinv * (T)(1.0 / (R5 ? (double)rodas5pc::gamma : (double)rodas4c::gamma));
+#endif
         // W = J - mass_matrix * inv(dtgamma) (gpu_rodas5P_perform_step.jl:81-82, 238-239); every
         // `mass_matrix * (dtC.. * k..)` below goes through MASSV (identity: nothing happens)
         constexpr bool MASS = has_mass_of<Model>::value;
@@ -319,14 +348,14 @@ struct Rodas {
         }
 #define MASSV(v) do { if constexpr (MASS) { T mv_[N]; mass_mul<T, N>(Mm, v, mv_); DEGK_UNROLL for (int c_ = 0; c_ < N; ++c_) v[c_] = mv_[c_]; } } while (0)
         T cs[N];
-        LinSolve<T, N> F;
+        LinSolve<T, N, true> F;
         if (!F.factor(J)) return false;
         T (&k)[NS][N] = K.ks;
         T du[N], lt[N], uu[N];
         Model::template f<T>(du, uprev, p, t);
         // Step 1
         { const T dtd1 = h * RC(d1);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = du[c] + dtd1 * dT[c]; }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = DTD_(du[c], dtd1, c); }
         F.solve_neg(lt, k[0]);
         DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = uprev[c] + RC(a21) * k[0][c];
         Model::template f<T>(du, uu, p, t + RC(c2) * h);
@@ -334,7 +363,7 @@ struct Rodas {
         { const T dtd2 = h * RC(d2), C21 = CH_(RC(C21));
           DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_(C21 * k[0][c]);
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd2 * dT[c]) + cs[c]; }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = DTD_(du[c], dtd2, c) + cs[c]; }
         F.solve_neg(lt, k[1]);
         DEGK_UNROLL for (int c = 0; c < N; ++c) uu[c] = (uprev[c] + RC(a31) * k[0][c]) + RC(a32) * k[1][c];
         Model::template f<T>(du, uu, p, t + RC(c3) * h);
@@ -342,7 +371,7 @@ struct Rodas {
         { const T dtd3 = h * RC(d3), C31 = CH_(RC(C31)), C32 = CH_(RC(C32));
           DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_((C31 * k[0][c] + C32 * k[1][c]));
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd3 * dT[c]) + cs[c]; }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = DTD_(du[c], dtd3, c) + cs[c]; }
         F.solve_neg(lt, k[2]);
         DEGK_UNROLL for (int c = 0; c < N; ++c)
             uu[c] = ((uprev[c] + RC(a41) * k[0][c]) + RC(a42) * k[1][c]) + RC(a43) * k[2][c];
@@ -351,7 +380,7 @@ struct Rodas {
         { const T dtd4 = h * RC(d4), C41 = CH_(RC(C41)), C42 = CH_(RC(C42)), C43 = CH_(RC(C43));
           DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_(((C41 * k[0][c] + C42 * k[1][c]) + C43 * k[2][c]));
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd4 * dT[c]) + cs[c]; }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = DTD_(du[c], dtd4, c) + cs[c]; }
         F.solve_neg(lt, k[3]);
         DEGK_UNROLL for (int c = 0; c < N; ++c)
             uu[c] = (((uprev[c] + RC(a51) * k[0][c]) + RC(a52) * k[1][c]) + RC(a53) * k[2][c]) + RC(a54) * k[3][c];
@@ -362,7 +391,7 @@ struct Rodas {
             { const T dtd5 = h * R5C(d5);
               DEGK_UNROLL for (int c = 0; c < N; ++c) cs[c] = CSC_((((C52 * k[1][c] + C54 * k[3][c]) + C51 * k[0][c]) + C53 * k[2][c]));
           MASSV(cs);
-          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = (du[c] + dtd5 * dT[c]) + cs[c]; }
+          DEGK_UNROLL for (int c = 0; c < N; ++c) lt[c] = DTD_(du[c], dtd5, c) + cs[c]; }
             F.solve_neg(lt, k[4]);
             DEGK_UNROLL for (int c = 0; c < N; ++c)
                 uu[c] = ((((uprev[c] + R5C(a61) * k[0][c]) + R5C(a62) * k[1][c]) + R5C(a63) * k[2][c]) +
@@ -414,6 +443,7 @@ struct Rodas {
         }
 #undef CH_
 #undef CSC_
+#undef DTD_
         if (WANT_ERR) {
             DEGK_UNROLL for (int c = 0; c < N; ++c) err[c] = k[NS - 1][c];
         }
