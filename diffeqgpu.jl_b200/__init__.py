@@ -20,7 +20,7 @@ from .algorithms import (EnsembleGPUKernel, GPUEM, GPUKvaerno3, GPUKvaerno5, GPU
                          GPUTsit5, GPUVern7, GPUVern9, alg_order)
 from .callbacks import (CallbackSet, ContinuousCallback, DiscreteCallback, GPUContinuousCallback,
                         GPUDiscreteCallback)
-from .lowerlevel_solve import Range, get_program, vectorized_asolve, vectorized_solve
+from .lowerlevel_solve import Range, SolvePlan, get_program, vectorized_asolve, vectorized_solve
 from .problems import (EnsembleContext, EnsembleProblem, ODEFunction, ODEProblem, ProblemBatch,
                        SDEFunction, SDEProblem, adapt, make_prob_compatible, remake)
 from .solve import EnsembleSolution, ODESolution, solve, solve_host
@@ -30,7 +30,7 @@ __all__ = [
     "DegkError", "EnsembleGPUKernel", "GPUEM", "GPUODEAlgorithm", "GPUODEImplicitAlgorithm",
     "GPURodas4", "GPURodas5P", "GPURosenbrock23", "GPUSDEAlgorithm", "GPUSIEA", "GPUTsit5",
     "GPUVern7", "GPUVern9", "alg_order", "Range", "get_program", "vectorized_asolve",
-    "vectorized_solve", "EnsembleContext", "EnsembleProblem", "ODEFunction", "ODEProblem",
+    "vectorized_solve", "SolvePlan", "EnsembleContext", "EnsembleProblem", "ODEFunction", "ODEProblem",
     "ProblemBatch", "SDEFunction", "SDEProblem", "adapt", "make_prob_compatible", "remake",
     "EnsembleSolution", "ODESolution", "solve", "solve_host", "models", "EnsembleMoments", "MomentsSolution", "solve_moments",
     "GPUKvaerno3", "GPUKvaerno5", "CallbackSet", "ContinuousCallback", "GPUContinuousCallback", "DiscreteCallback", "GPUDiscreteCallback",

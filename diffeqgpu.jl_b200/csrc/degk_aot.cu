@@ -71,9 +71,14 @@ using namespace degk;
         (int)sizeof(SaveRec<T, MD::N>)
 #define NOV2 nullptr, 0, 0, 0
 #define LS(T, MD, METHOD, W) (const void*)&k_ode_lockstep<DEGK_STRICT, T, MD, METHOD, W>, W
+#if DEGK_STRICT
+#define LS1(T, MD, METHOD) nullptr
+#else
+#define LS1(T, MD, METHOD) (const void*)&k_ode_lockstep<DEGK_STRICT, T, MD, METHOD, 1>
+#endif
 // explicit RK: packed pairs for Float32 in fast mode
 #define ODE_ERK(NAME, MD, METHOD, ALG)                                                              \
-    {NAME, ALG, 0, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, float, MD, METHOD>, NOV2, LS(float, MD, METHOD, WF32)},    \
+    {NAME, ALG, 0, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, float, MD, METHOD>, NOV2, LS(float, MD, METHOD, WF32), LS1(float, MD, METHOD)},    \
     {NAME, ALG, 0, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, float, MD, METHOD>, V2(float, MD, METHOD, WF32)}, \
     {NAME, ALG, 1, 0, DIMS(MD), (const void*)&k_ode_solve<DEGK_STRICT, double, MD, METHOD>, NOV2, LS(double, MD, METHOD, 1)},   \
     {NAME, ALG, 1, 1, DIMS(MD), (const void*)&k_ode_asolve<DEGK_STRICT, double, MD, METHOD>, V2(double, MD, METHOD, 1)},

@@ -75,10 +75,15 @@ size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged) {
 
 // dynamic shared memory of the lock-step kernel in the reference layout (degk_ode_lockstep.cuh, lockstep_smem_bytes):
 // per warp 32 w buffers of 32 / w rows (rounded up to a multiple of four values, plus four) and the ring of save times
-size_t degk_lockstep_smem_bytes(const degk_program* prog) {
+// largest staging area the lock-step kernel may ask for (bytes per block)
+size_t degk_lockstep_smem_max() {
+    static const size_t v = [] { const char* e = getenv("DEGK_LOCKSTEP_SMEM_MAX"); return e ? (size_t)atoll(e) : (size_t)DEGK_LOCKSTEP_SMEM_MAX; }();
+    return v;
+}
+size_t degk_lockstep_smem_bytes(const degk_program* prog, int w) {
     const size_t es = dtype_size(prog->info.dtype);
-    const int rows = 32 / std::max(1, prog->w3);                  // lockstep_ring_rows
-    return (size_t)(DEGK_BLOCK2 / 32) * ((size_t)32 * prog->w3 * (size_t)(((prog->info.n_state * rows + 3) & ~3) + 4) + (size_t)rows) * es;
+    const int rows = 32 / std::max(1, w);                         // lockstep_ring_rows
+    return (size_t)(DEGK_BLOCK2 / 32) * ((size_t)32 * w * (size_t)(((prog->info.n_state * rows + 3) & ~3) + 4) + (size_t)rows) * es;
 }
 
 extern "C" int degk_version(void) { return DEGK_VERSION; }
@@ -201,7 +206,7 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
         } else {
             prog->fn[0] = e0->fn;
             prog->fn[1] = e1 ? e1->fn : nullptr;
-            if (e0->fn3) { prog->fn[3] = e0->fn3; prog->w3 = e0->w3; }
+            if (e0->fn3) { prog->fn[3] = e0->fn3; prog->w3 = e0->w3; prog->fn[4] = e0->fn4; }
             if (e1 && e1->fn2) {
                 prog->fn[2] = e1->fn2;
                 prog->w2 = e1->w2; prog->qcap2 = e1->qcap2; prog->rec_bytes2 = e1->rec_bytes2;
@@ -225,10 +230,11 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
             const void* fo = prog->fn[1] ? prog->fn[1] : prog->fn[0];
             CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fo, DEGK_BLOCK, 0));
             prog->info.max_blocks_per_sm = occ;
-            if (prog->fn[3]) {
-                const size_t ls_smem = degk_lockstep_smem_bytes(prog);
-                if (ls_smem > 48 * 1024 && ls_smem <= 64 * 1024)
-                    CK(ctx, cudaFuncSetAttribute(prog->fn[3], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
+            for (int k = 3; k <= 4; ++k) {
+                if (!prog->fn[k]) continue;
+                const size_t ls_smem = degk_lockstep_smem_bytes(prog, k == 3 ? prog->w3 : 1);
+                if (ls_smem > 48 * 1024 && ls_smem <= degk_lockstep_smem_max())
+                    CK(ctx, cudaFuncSetAttribute(prog->fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls_smem));
             }
             if (prog->fn[2]) {
                 cudaFuncAttributes fa;
@@ -418,23 +424,36 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
                     stageable && (prog->info.is_jit ? prog->jit_fn[2] != nullptr : prog->fn[2] != nullptr);
     if (prog->has_events) sched = k.schedule = DEGK_SCHED_STATIC;   // one thread per trajectory
     // fixed dt, one (t0, tf, dt) for the whole launch, every-step saves, explicit RK stepper: the lock-step kernel
-    // (degk_ode_lockstep.cuh).  By default only for launches that fill the GPU with it -- with a few warps per SM
-    // the run is latency-bound and one trajectory per thread on more SMs is faster (C1 at N = 10^4).
+    // (degk_ode_lockstep.cuh) at every ensemble size -- its warp-uniform loop is also the shorter dependent chain of a
+    // latency-bound small launch (C1 at N = 10^4: 26 us against 60 us, profiles/r2g_c1_sizes.md).
     const bool has_ls = prog->info.is_jit ? prog->jit_fn[3] != nullptr : prog->fn[3] != nullptr;
     const bool ls = which == 0 && has_ls && !prog->is_sde && !prog->has_events && a->engine != DEGK_ENGINE_V1 && !a->saveat &&
                     a->save_everystep && a->tspan_stride == 0 && !a->dae_init && a->n_tstops == 0 && !a->reduce &&
-                    (a->engine == DEGK_ENGINE_LOCKSTEP || a->n_traj >= (long long)ctx->sm_count * DEGK_BLOCK2 * prog->w3 * 2) &&
+                    // (reference layout with a state too large for the staging area: its scattered stores lose to the
+                    //  one-thread-per-trajectory kernel with staged saves once the launch fills the GPU)
+                    (a->engine == DEGK_ENGINE_LOCKSTEP || a->out_layout != DEGK_LAYOUT_REF ||
+                     degk_lockstep_smem_bytes(prog, 1) <= degk_lockstep_smem_max() ||
+                     a->n_traj < (long long)ctx->sm_count * DEGK_BLOCK * 3) &&
                     !getenv("DEGK_NO_LOCKSTEP");
+    // Where the build carries two trajectories per thread (fast Float32) there is a one-per-thread twin: a launch that
+    // does not fill the GPU is latency-bound, and a dependent chain of packed FMAs runs at half the rate of a scalar
+    // one (trajectory-major layout: packed pairs win from ~2 * 10^5 trajectories); with the staged flush of the
+    // reference layout the twin is faster at every size (10^6: 138.8 against 133.9 G steps/s)
+    const bool ls_staged = ls && a->out_layout == DEGK_LAYOUT_REF && degk_lockstep_smem_bytes(prog, 1) <= degk_lockstep_smem_max();
+    long long w1_below = ls_staged ? (1LL << 62) : (long long)ctx->sm_count * DEGK_BLOCK2 * 2 * DEGK_LOCKSTEP_W1_FILL;
+    if (const char* e = getenv("DEGK_LOCKSTEP_W1_BELOW")) w1_below = atoll(e);
+    const bool ls1 = ls && !prog->info.is_jit && prog->fn[4] && prog->w3 > 1 && a->n_traj < w1_below;
+    const int wls = ls1 ? 1 : prog->w3;
     const int block = (v2 || ls) ? DEGK_BLOCK2 : DEGK_BLOCK;
-    const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : (ls ? DEGK_BLOCK2 * prog->w3 : DEGK_BLOCK);
+    const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : (ls ? DEGK_BLOCK2 * wls : DEGK_BLOCK);
     size_t smem = 0;
     if (v2) smem = degk_smem2_bytes(prog, a->saveat ? a->n_saveat : 0);
     if (ls) {
         // reference layout: a 32 / w-row buffer per trajectory in shared memory, flushed in sector-aligned pieces
         // (degk_ode_lockstep.cuh); the trajectory-major layout needs no staging (lanes already write consecutive
         // addresses), and states too large for the rings go out unstaged as well
-        const size_t ring_bytes = degk_lockstep_smem_bytes(prog);
-        if (a->out_layout == DEGK_LAYOUT_REF && ring_bytes <= 64 * 1024) {
+        const size_t ring_bytes = degk_lockstep_smem_bytes(prog, wls);
+        if (a->out_layout == DEGK_LAYOUT_REF && ring_bytes <= degk_lockstep_smem_max()) {
             k.stage_rows = 16;
             smem = ring_bytes;
         }
@@ -466,7 +485,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     }
     if (blocks > 2147483647LL) { degk_set_error(ctx, "too many blocks"); return DEGK_ERR_INVALID; }
 
-    const int kidx = v2 ? 2 : (ls ? 3 : which);
+    const int kidx = v2 ? 2 : (ls ? (ls1 ? 4 : 3) : which);
     int rc = DEGK_OK;
     if (prog->info.is_jit) {
         rc = degk_jit_launch(prog, kidx, (unsigned)blocks, (unsigned)block, (unsigned)smem, &k, stream);

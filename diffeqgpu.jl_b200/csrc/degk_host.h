@@ -40,16 +40,17 @@ struct degk_program {
     bool is_sde = false;
     bool has_events = false;                  // built with the tstops / callback kernel pair (degk_ode_events.cuh)
     // AOT kernels: [0] fixed-dt / SDE, [1] adaptive v1, [2] adaptive v2, [3] lock-step fixed-dt
-    const void* fn[4] = {nullptr, nullptr, nullptr, nullptr};
+    const void* fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // 4: lock-step, one trajectory per thread (fast Float32 build)
     int w2 = 0, qcap2 = 0, rec_bytes2 = 0;             // geometry of the v2 kernel (see degk_internal.h)
     int w3 = 0;                               // trajectories per thread of the lock-step kernel
     void* jit_module = nullptr;               // CUmodule
-    void* jit_fn[4] = {nullptr, nullptr, nullptr, nullptr};     // CUfunction, same indexing as fn
+    void* jit_fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // CUfunction, same indexing as fn
 };
 
 void degk_set_error(degk_ctx* ctx, const char* fmt, ...);
 size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged);
-size_t degk_lockstep_smem_bytes(const degk_program* prog);
+size_t degk_lockstep_smem_bytes(const degk_program* prog, int w);
+size_t degk_lockstep_smem_max();
 
 // NVRTC path (degk_jit.cpp)
 int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog);

@@ -2,6 +2,14 @@
 #pragma once
 
 #define DEGK_BLOCK 256    // threads per block of the first-generation kernels (__launch_bounds__)
+#ifndef DEGK_LOCKSTEP_W1_FILL
+#define DEGK_LOCKSTEP_W1_FILL 6   // lock-step launches below this many 2-trajectory blocks per SM run one trajectory per thread (measured)
+#endif
+#ifndef DEGK_LOCKSTEP_SMEM_MAX
+// staging area of the lock-step kernel per block: up to half an SM's shared memory (two blocks per SM).  Measured at 10^6
+// trajectories: Henon-Heiles Float32 (67.6 KB) 4.2 ms unstaged -> 1.06 ms staged, Lorenz Float64 (103 KB) 4.5 -> 1.56 ms
+#define DEGK_LOCKSTEP_SMEM_MAX (112 * 1024)
+#endif
 #ifndef DEGK_BLOCK2
 #define DEGK_BLOCK2 128   // threads per block of the adaptive kernel (degk_ode_kernels4.cuh)
 #endif
@@ -22,4 +30,7 @@ struct degk_aot_entry {
     // lock-step fixed-dt kernel (degk_ode_lockstep.cuh): uniform (t0, tf, dt), every-step saves; null if none
     const void* fn3;
     int w3;         // trajectories per thread of fn3 (1 or 2)
+    // the same kernel with one trajectory per thread where fn3 carries two (fast Float32 build): launches too small
+    // to fill the GPU are latency-bound, and a dependent FFMA2 chain runs at half the rate of a scalar one; else null
+    const void* fn4;
 };

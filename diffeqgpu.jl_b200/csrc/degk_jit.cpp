@@ -390,8 +390,8 @@ static int make_source(degk_ctx* ctx, const degk_model_desc* d, int slots, std::
             snprintf(buf, sizeof buf,
                      "extern \"C\" __global__ void __launch_bounds__(%d, (degk::lockstep_minblocks<REAL>())) degk_jit_lockstep(const degk::KArgs a) {\n"
                      "    extern __shared__ __align__(16) unsigned char degk_smem[];\n"
-                     "    degk::ode_solve_lockstep_body<REAL, MODEL, METHODT, %d>(a, degk_smem);\n}\n",
-                     DEGK_BLOCK2, slots);
+                     "    degk::ode_solve_lockstep_body<REAL, MODEL, METHODT, 1>(a, degk_smem);\n}\n",
+                     DEGK_BLOCK2);     // one trajectory per thread: faster in the reference layout at every size (degk_api.cu)
             src += buf;
         }
     }
@@ -493,11 +493,11 @@ int degk_jit_build(degk_ctx* ctx, const degk_model_desc* d, degk_program* prog) 
         CUfunction f3 = nullptr;
         DRV(ctx, g_drv.ModuleGetFunction(&f3, mod, "degk_jit_lockstep"));
         prog->jit_fn[3] = f3;
-        prog->w3 = slots;
+        prog->w3 = 1;
         prog->info.dtype = d->dtype;
         prog->info.n_state = d->rhs_src ? d->n_state : builtin_n_state(d->builtin);
-        const size_t ls_smem = degk_lockstep_smem_bytes(prog);
-        if (ls_smem > 48 * 1024 && ls_smem <= 64 * 1024)
+        const size_t ls_smem = degk_lockstep_smem_bytes(prog, prog->w3);
+        if (ls_smem > 48 * 1024 && ls_smem <= degk_lockstep_smem_max())
             DRV(ctx, g_drv.FuncSetAttribute(f3, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)ls_smem));
     }
     prog->info.is_jit = 1;

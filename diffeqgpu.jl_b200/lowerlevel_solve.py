@@ -139,7 +139,7 @@ def _ptr(t):
 
 def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_everystep, n_rows,
             fp_mode, schedule, layout, stats, stream, traj_offset=0, reduce=None, engine="auto",
-            callback=None, tstops=None, sort_by=None):
+            callback=None, tstops=None, sort_by=None, prepare=False):
     if not isinstance(probs, ProblemBatch):
         probs = adapt("cuda", probs)
     dev = probs.device
@@ -210,22 +210,78 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
         a.max_iters = int(__import__("os").environ.get("DEGK_MAX_ITERS", "0"))   # 0 => library default (1e7 attempts per trajectory when adaptive, none for fixed dt)
         a.engine = _lib.ENGINES[engine]
         a.dae_init = int(bool(getattr(prob.f, "initialize", False))) if isinstance(prob, ODEProblem) else 0
-        prog.solve(a, launch_stream.cuda_stream)
         for buf in (probs.u0, probs.p, probs.tspan, reduce):     # inputs made on other streams stay alive until this one is done
             if isinstance(buf, torch.Tensor) and buf.is_cuda and buf.numel():
                 buf.record_stream(launch_stream)
         # keep inputs alive until the stream has consumed them
         us._degk_keepalive = (probs, d_saveat, d_tstops, d_order)
-    if stats:
-        return ts, us, out
-    return ts, us
+        plan = SolvePlan(prog, a, dev, launch_stream, ts, us, out if stats else None, reduce)
+        if prepare:
+            return plan
+        plan._launch()
+    return plan.result()
+
+
+class SolvePlan:
+    """A prepared launch: program, marshalled `degk_solve_args` and output arrays of one `vectorized_solve` /
+    `vectorized_asolve` call (`prepare=True`).  Calling the plan launches the kernel again into the same output arrays;
+    the host side of a call is one ctypes call (a few microseconds instead of ~0.1 ms of argument conversion and
+    allocation), which is what a small ensemble (BASELINE config 1: 10^4 trajectories, a ~30 us kernel) is bound by.
+    `capture(k)` records k back-to-back launches in a CUDA graph, `replay()` launches that graph.
+    The reference has no counterpart (every `solve` allocates and launches, lowerlevel_solve.jl:53-131)."""
+
+    def __init__(self, prog, args, dev, stream, ts, us, stats, reduce):
+        self.prog, self.args, self.device, self.stream = prog, args, dev, stream
+        self.ts, self.us, self.stats, self.reduce = ts, us, stats, reduce
+        self._graph = None
+
+    def result(self):
+        return (self.ts, self.us, self.stats) if self.stats is not None else (self.ts, self.us)
+
+    def _launch(self):
+        self.prog.solve(self.args, self.stream.cuda_stream)
+
+    def _reset(self):
+        if self.stats is not None:
+            self.stats["totals"].zero_()                 # the kernels add to the totals
+        if self.reduce is not None:
+            self.reduce.zero_()
+
+    def __call__(self):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self._reset()
+            self._launch()
+        return self.result()
+
+    def capture(self, launches=1):
+        """Record `launches` launches in a CUDA graph (the plan must have run once: the first launch of a program
+        sets kernel attributes, which stream capture does not allow)."""
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(self.stream)
+        saved = self.stream
+        with torch.cuda.device(self.device), torch.cuda.graph(g, stream=side):
+            self.stream = torch.cuda.current_stream(self.device)
+            for _ in range(int(launches)):
+                self._reset()
+                self._launch()
+        self.stream = saved
+        self._graph = g
+        return self
+
+    def replay(self):
+        if self._graph is None:
+            raise RuntimeError("capture() first")
+        self._graph.replay()
+        return self.result()
 
 
 def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, debug=False,
                      callback=None, tstops=None, fp_mode="strict", schedule="auto", layout="ref",
-                     stats=False, stream=None, traj_offset=0, reduce=None, engine="auto", **kwargs):
+                     stats=False, stream=None, traj_offset=0, reduce=None, engine="auto", prepare=False, **kwargs):
     """Fixed-step batched solve; returns (ts, us) on the device (add `stats=True` for
     per-trajectory retcode/naccept/nreject and totals, which the reference does not have).
+    `prepare=True` returns a `SolvePlan` instead of launching (re-launch with `plan()`).
     `engine`: "auto" (the lock-step kernel for large launches with one tspan, every-step saves and an explicit RK
     stepper, else one thread per trajectory), "lockstep" (whenever its preconditions hold), "v1" (never)."""
     if not isinstance(alg, GPUODEAlgorithm):
@@ -256,14 +312,15 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
     return _launch(probs, prob, alg, dt=dt, adaptive=False, abstol=0.0, reltol=0.0, saveat=saveat_c,
                    save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
                    schedule=schedule, layout=layout, stats=stats, stream=stream,
-                   traj_offset=traj_offset, reduce=reduce, callback=callback, tstops=tstops, engine=engine)
+                   traj_offset=traj_offset, reduce=reduce, callback=callback, tstops=tstops, engine=engine,
+                   prepare=prepare)
 
 
 def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save_everystep=False,
                       abstol=np.float32(1e-6), reltol=np.float32(1e-3), debug=False, callback=None,
                       tstops=None, fp_mode="strict", schedule="auto", layout="ref", stats=False,
-                      stream=None, engine="auto", sort_by=None, **kwargs):
-    """Adaptive batched solve (defaults as lowerlevel_solve.jl:253-260)."""
+                      stream=None, engine="auto", sort_by=None, prepare=False, **kwargs):
+    """Adaptive batched solve (defaults as lowerlevel_solve.jl:253-260).  `prepare=True`: see vectorized_solve."""
     if isinstance(prob, SDEProblem):
         raise RuntimeError("Adaptive time-stepping is not supported yet with GPUEM.")   # :348-356
     if not isinstance(alg, GPUODEAlgorithm) or isinstance(alg, GPUSDEAlgorithm):
@@ -288,4 +345,4 @@ def vectorized_asolve(probs, prob, alg, *, dt=np.float32(0.1), saveat=None, save
     return _launch(probs, prob, alg, dt=dt, adaptive=True, abstol=abstol, reltol=reltol,
                    saveat=saveat_c, save_everystep=save_everystep, n_rows=n_rows, fp_mode=fp_mode,
                    schedule=schedule, layout=layout, stats=stats, stream=stream, engine=engine,
-                   callback=callback, tstops=tstops, sort_by=sort_by)
+                   callback=callback, tstops=tstops, sort_by=sort_by, prepare=prepare)

@@ -39,6 +39,13 @@ for fp in ("fast", "strict"):
     pr64 = dg.ODEProblem(dg.models.lorenz, np.array([1.0, 0, 0]), (0.0, 2.0), np.array([10, 28, 8 / 3]))
     pb64 = dg.ProblemBatch.from_arrays(pr64, p=lorenz_sweep(333, seed=4).astype(np.float64), device="cuda:0")
     dg.vectorized_solve(pb64, pr64, dg.GPUTsit5(), dt=0.05, fp_mode=fp, engine="lockstep")
+    from cases import henon_heiles_u0  # noqa: E402
+    for n_hh in (61, 1300):                  # 4-state Float32 (67.6 KB of staging per block) and its prepared-plan relaunch
+        u0h = henon_heiles_u0(n_hh).astype(f32)
+        prh = dg.ODEProblem(dg.models.henon_heiles, u0h[0], (0.0, 4.3), None)
+        pbh = dg.ProblemBatch.from_arrays(prh, u0=u0h, device="cuda:0")
+        plan = dg.vectorized_solve(pbh, prh, dg.GPUTsit5(), dt=f32(0.1), fp_mode=fp, prepare=True)
+        plan(); plan()
     sp = dg.SDEProblem(dg.models.lorenz_additive, np.array([1, 0, 0], f32), (0.0, 0.05), np.array([10, 28, 8 / 3], f32), seed=5)
     dg.solve(dg.EnsembleProblem(sp, reduction=dg.EnsembleMoments()), dg.GPUEM(), dg.EnsembleGPUKernel(dev="cuda:0", fp_mode=fp),
              trajectories=1001, dt=f32(1e-3), save_everystep=False, adaptive=False)
