@@ -52,6 +52,16 @@ def main():
             probs = dg.ProblemBatch.from_arrays(prob, p=p, device=dev)
             ms, o = timed(lambda: dg.vectorized_solve(probs, prob, dg.GPUTsit5(), dt=np.float32(0.1), fp_mode=fp, stats=True))
             out.append(report(f"C1 Lorenz Tsit5 fixed dt=0.1 f32 N={N} {fp}", ms, o[2], 190))
+        # C2 at the lower end of its size range (the bench line is 10^8 per GPU)
+        for N in (1_000_000, 10_000_000):
+            p = torch.rand((N, 3), generator=g, device=dev) * torch.tensor(P0, dtype=torch.float32, device=dev)
+            prob = dg.ODEProblem(dg.models.lorenz, np.array([1, 0, 0], np.float32), (0.0, 10.0), P0.astype(np.float32))
+            probs = dg.ProblemBatch.from_arrays(prob, p=p, device=dev)
+            sv = np.arange(0, 11, dtype=np.float32)
+            ms, o = timed(lambda: dg.vectorized_asolve(probs, prob, dg.GPUTsit5(), dt=np.float32(0.1), abstol=np.float32(1e-6),
+                                                       reltol=np.float32(1e-6), saveat=sv, fp_mode=fp, stats=True))
+            out.append(report(f"C2 Lorenz Tsit5 adaptive tol 1e-6 saveat 0:1:10 f32 N={N} {fp}", ms, o[2], 263))
+            del probs, p
         # C3: Vern9 adaptive f64 tol 1e-10
         N = 1_000_000
         p64 = (torch.rand((N, 3), generator=g, device=dev).double()) * torch.tensor(P0, dtype=torch.float64, device=dev)
