@@ -68,8 +68,9 @@ using namespace degk;
 #define DIMS(MD) MD::N, MD::NP, MD::M, MD::NOISE
 #define V2(T, MD, METHOD, W)                                                                        \
     (const void*)&k_ode_asolve2<DEGK_STRICT, T, MD, METHOD, W>, W, asolve4_qcap<T, MD::N, W>(),     \
-        (int)sizeof(SaveRec<T, MD::N>)
-#define NOV2 nullptr, 0, 0, 0
+        (int)sizeof(SaveRec<T, MD::N>),                                                             \
+        ((W) > 1 ? (const void*)&k_ode_asolve2<DEGK_STRICT, T, MD, METHOD, 1> : (const void*)nullptr), asolve4_qcap<T, MD::N, 1>()
+#define NOV2 nullptr, 0, 0, 0, nullptr, 0
 #define LS(T, MD, METHOD, W) (const void*)&k_ode_lockstep<DEGK_STRICT, T, MD, METHOD, W>, W
 #if DEGK_STRICT
 #define LS1(T, MD, METHOD) nullptr

@@ -66,10 +66,11 @@ static size_t dtype_size(int dtype) { return dtype == DEGK_F64 ? 8 : 4; }
 
 // dynamic shared memory of the adaptive kernel (degk_ode_kernels4.cuh, asolve4_smem_bytes):
 // per-warp save queues + per-warp problem pools (32 x (n + np + 3) values) + saveat copy
-size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged) {
+size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged, int qcap) {
+    if (qcap <= 0) qcap = prog->qcap2;
     const size_t es = dtype_size(prog->info.dtype);
     const size_t nw = DEGK_BLOCK2 / 32;
-    return nw * prog->qcap2 * prog->rec_bytes2 + nw * 32 * (size_t)(prog->info.n_state + prog->info.n_param + 3) * es +
+    return nw * qcap * prog->rec_bytes2 + nw * 32 * (size_t)(prog->info.n_state + prog->info.n_param + 3) * es +
            ((size_t)n_saveat_staged + 2) * es;     // + two +inf sentinels
 }
 
@@ -210,6 +211,7 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
             if (e1 && e1->fn2) {
                 prog->fn[2] = e1->fn2;
                 prog->w2 = e1->w2; prog->qcap2 = e1->qcap2; prog->rec_bytes2 = e1->rec_bytes2;
+                prog->fn[5] = e1->fn2b; prog->qcap2b = e1->qcap2b;
             }
             prog->info.n_state = e0->n_state; prog->info.n_param = e0->n_param;
             prog->info.n_noise = e0->n_noise; prog->info.noise_kind = e0->noise_kind;
@@ -246,6 +248,12 @@ extern "C" int degk_program_build(degk_ctx* ctx, const degk_model_desc* d, degk_
                 if (smem_max > 48 * 1024) CK(ctx, cudaFuncSetAttribute(prog->fn[2], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
                 CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prog->fn[2], DEGK_BLOCK2, smem));
                 prog->info.max_blocks_per_sm2 = occ;
+                if (prog->fn[5]) {
+                    const size_t smem_b = degk_smem2_bytes(prog, 1024, prog->qcap2b), smem_b_max = degk_smem2_bytes(prog, DEGK_SAVEAT_STAGE_MAX, prog->qcap2b);
+                    if (smem_b_max > 48 * 1024) CK(ctx, cudaFuncSetAttribute(prog->fn[5], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b_max));
+                    CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prog->fn[5], DEGK_BLOCK2, smem_b));
+                    prog->max_blocks_per_sm2b = occ;
+                }
             }
         }
     }
@@ -445,9 +453,14 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     const bool ls1 = ls && !prog->info.is_jit && prog->fn[4] && prog->w3 > 1 && a->n_traj < w1_below;
     const int wls = ls1 ? 1 : prog->w3;
     const int block = (v2 || ls) ? DEGK_BLOCK2 : DEGK_BLOCK;
-    const int per_block = v2 ? DEGK_BLOCK2 * prog->info.slots_per_thread2 : (ls ? DEGK_BLOCK2 * wls : DEGK_BLOCK);
+    // the adaptive kernel has the same twin: below DEGK_ADAPTIVE_W1_FILL resident two-trajectory launches' worth of work
+    // the one-per-thread form is faster (profiles/r2g_c2_sizes.md)
+    long long v2b_below = (long long)ctx->sm_count * DEGK_BLOCK2 * 2 * std::max(1, prog->info.max_blocks_per_sm2) * DEGK_ADAPTIVE_W1_FILL;
+    if (const char* e = getenv("DEGK_ADAPTIVE_W1_BELOW")) v2b_below = atoll(e);
+    const bool v2b = v2 && !prog->info.is_jit && prog->fn[5] && prog->w2 > 1 && a->n_traj < v2b_below;
+    const int per_block = v2 ? DEGK_BLOCK2 * (v2b ? 1 : prog->info.slots_per_thread2) : (ls ? DEGK_BLOCK2 * wls : DEGK_BLOCK);
     size_t smem = 0;
-    if (v2) smem = degk_smem2_bytes(prog, a->saveat ? a->n_saveat : 0);
+    if (v2) smem = degk_smem2_bytes(prog, a->saveat ? a->n_saveat : 0, v2b ? prog->qcap2b : 0);
     if (ls) {
         // reference layout: a 32 / w-row buffer per trajectory in shared memory, flushed in sector-aligned pieces
         // (degk_ode_lockstep.cuh); the trajectory-major layout needs no staging (lanes already write consecutive
@@ -477,7 +490,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     }
     long long blocks = (a->n_traj + per_block - 1) / per_block;
     if (sched == DEGK_SCHED_QUEUE) {
-        long long resident = (long long)ctx->sm_count * std::max(1, v2 ? prog->info.max_blocks_per_sm2 : prog->info.max_blocks_per_sm);
+        long long resident = (long long)ctx->sm_count * std::max(1, v2 ? (v2b ? prog->max_blocks_per_sm2b : prog->info.max_blocks_per_sm2) : prog->info.max_blocks_per_sm);
         if (blocks > resident) blocks = resident;
         unsigned slot = ctx->next_counter.fetch_add(1) % DEGK_NCOUNTERS;
         k.work_counter = ctx->d_counters + slot;
@@ -485,7 +498,7 @@ static int launch(degk_program* prog, const degk_solve_args* a, cudaStream_t str
     }
     if (blocks > 2147483647LL) { degk_set_error(ctx, "too many blocks"); return DEGK_ERR_INVALID; }
 
-    const int kidx = v2 ? 2 : (ls ? (ls1 ? 4 : 3) : which);
+    const int kidx = v2 ? (v2b ? 5 : 2) : (ls ? (ls1 ? 4 : 3) : which);
     int rc = DEGK_OK;
     if (prog->info.is_jit) {
         rc = degk_jit_launch(prog, kidx, (unsigned)blocks, (unsigned)block, (unsigned)smem, &k, stream);

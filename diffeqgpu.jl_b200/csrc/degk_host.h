@@ -40,15 +40,16 @@ struct degk_program {
     bool is_sde = false;
     bool has_events = false;                  // built with the tstops / callback kernel pair (degk_ode_events.cuh)
     // AOT kernels: [0] fixed-dt / SDE, [1] adaptive v1, [2] adaptive v2, [3] lock-step fixed-dt
-    const void* fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // 4: lock-step, one trajectory per thread (fast Float32 build)
+    const void* fn[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 4 / 5: lock-step / adaptive kernel, one trajectory per thread (fast Float32 build)
     int w2 = 0, qcap2 = 0, rec_bytes2 = 0;             // geometry of the v2 kernel (see degk_internal.h)
+    int qcap2b = 0, max_blocks_per_sm2b = 0;           // ... of its one-trajectory-per-thread twin fn[5]
     int w3 = 0;                               // trajectories per thread of the lock-step kernel
     void* jit_module = nullptr;               // CUmodule
-    void* jit_fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // CUfunction, same indexing as fn
+    void* jit_fn[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     // CUfunction, same indexing as fn
 };
 
 void degk_set_error(degk_ctx* ctx, const char* fmt, ...);
-size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged);
+size_t degk_smem2_bytes(const degk_program* prog, int n_saveat_staged, int qcap = 0);
 size_t degk_lockstep_smem_bytes(const degk_program* prog, int w);
 size_t degk_lockstep_smem_max();
 

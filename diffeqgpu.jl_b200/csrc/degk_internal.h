@@ -5,6 +5,9 @@
 #ifndef DEGK_LOCKSTEP_W1_FILL
 #define DEGK_LOCKSTEP_W1_FILL 6   // lock-step launches below this many 2-trajectory blocks per SM run one trajectory per thread (measured)
 #endif
+#ifndef DEGK_ADAPTIVE_W1_FILL
+#define DEGK_ADAPTIVE_W1_FILL 5   // adaptive launches below this many resident two-trajectory grids (Lorenz Tsit5: 7.6e5 trajectories) run one trajectory per thread (measured, profiles/r2g_c2_sizes.md)
+#endif
 #ifndef DEGK_LOCKSTEP_SMEM_MAX
 // staging area of the lock-step kernel per block: up to half an SM's shared memory (two blocks per SM).  Measured at 10^6
 // trajectories: Henon-Heiles Float32 (67.6 KB) 4.2 ms unstaged -> 1.06 ms staged, Lorenz Float64 (103 KB) 4.5 -> 1.56 ms
@@ -27,6 +30,10 @@ struct degk_aot_entry {
     int w2;         // trajectories per thread of fn2 (1 or 2)
     int qcap2;      // save-queue capacity per warp (records)
     int rec_bytes2; // sizeof(SaveRec<T, N>)
+    // the same kernel with one trajectory per thread where fn2 carries two (fast Float32 build), for launches that do
+    // not fill the GPU (latency-bound: a dependent chain of packed FMAs runs at half the rate of a scalar one); else null
+    const void* fn2b;
+    int qcap2b;     // its save-queue capacity per warp
     // lock-step fixed-dt kernel (degk_ode_lockstep.cuh): uniform (t0, tf, dt), every-step saves; null if none
     const void* fn3;
     int w3;         // trajectories per thread of fn3 (1 or 2)

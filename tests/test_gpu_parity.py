@@ -164,8 +164,14 @@ def test_adaptive_other_solvers_bit_exact_f32(dg, oracle, alg):
     assert_bit_exact(g, r, alg + " endpoints")
 
 
-def test_fast_mode_within_tolerance(dg, oracle):
-    """The fast build (FMA-contracted, h-scaled stage sums, MUFU step control) is not bit-equal to the reference
+_FAST_REF = {}
+
+
+@pytest.mark.parametrize("width", ["one_per_thread", "packed_pairs"])
+def test_fast_mode_within_tolerance(dg, oracle, width, monkeypatch):
+    """(`width`: launches below ~7.6e5 trajectories run the fast build's one-trajectory-per-thread twin of the adaptive
+    kernel, larger ones the packed-pair kernel -- degk_api.cu; the environment variable pins either for this size.)
+    The fast build (FMA-contracted, h-scaled stage sums, MUFU step control) is not bit-equal to the reference
     arithmetic by construction, and on the chaotic part of the sweep a 1-ulp change is amplified by the dynamics
     (exactly as when the reference runs on another backend).  What is gated, on the WHOLE C2 sweep, per band of rho:
       * accuracy against a Float64 Vern9 ground truth (tol 1e-12): the fast build's error quantiles are within
@@ -178,19 +184,24 @@ def test_fast_mode_within_tolerance(dg, oracle):
       * everywhere: identical ts, Success, finite values.
     north_star's "10*reltol at every saveat point, identical step counts on >= 99 %" is met by the strict build
     (bit-identical); the fast build meets the bars above -- bench.py prints this class next to its number."""
+    monkeypatch.setenv("DEGK_ADAPTIVE_W1_BELOW", "0" if width == "packed_pairs" else str(1 << 40))
     p = lorenz_sweep(20000, seed=5)
     sv = np.arange(0, 11, dtype=f32)
     kw = dict(dt=0.1, adaptive=True, abstol=1e-6, reltol=1e-6, saveat=sv)
     g = gpu_solve(dg, "lorenz", "tsit5", U0_LORENZ, p, [0, 10], fp_mode="fast", **kw)
-    r = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 10], **kw)
+    if "r" not in _FAST_REF:
+        _FAST_REF["r"] = oracle.solve("lorenz", "tsit5", U0_LORENZ, p, [0, 10], **kw)
+    r = _FAST_REF["r"]
     assert np.array_equal(g["ts"], r["ts"]) and (g["retcode"] == 1).all() and np.isfinite(g["us"]).all()
     rho = p[:, 1]
     bands = [(0.0, 1.0), (1.0, 13.0), (13.0, 24.0), (24.0, 28.0)]
     report = []
     for lo, hi in bands:
         idx = np.nonzero((rho >= lo) & (rho < hi))[0][:1500]
-        truth = oracle.solve("lorenz", "vern9", U0_LORENZ, p[idx].astype(f64), [0, 10], dt=0.1, adaptive=True,
-                             abstol=1e-12, reltol=1e-12, saveat=sv.astype(f64), dtype=f64)["us"]
+        if ("truth", lo) not in _FAST_REF:
+            _FAST_REF[("truth", lo)] = oracle.solve("lorenz", "vern9", U0_LORENZ, p[idx].astype(f64), [0, 10], dt=0.1, adaptive=True,
+                                                    abstol=1e-12, reltol=1e-12, saveat=sv.astype(f64), dtype=f64)["us"]
+        truth = _FAST_REF[("truth", lo)]
         e_ref = np.abs(r["us"][idx] - truth).max(axis=(1, 2))
         e_fast = np.abs(g["us"][idx] - truth).max(axis=(1, 2))
         dn = np.abs(g["naccept"][idx].astype(int) - r["naccept"][idx].astype(int))
@@ -210,6 +221,29 @@ def test_fast_mode_within_tolerance(dg, oracle):
     assert (rel[calm] < 10 * 1e-6).mean() >= 0.85, q
     assert (rel[calm] < 100 * 1e-6).mean() >= 0.98, q
     print("fast-mode report (rho band, n, {q: (err fast, err ref)}, same count, +-1, within 2 %):", report)
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 65, 257, 4099])
+@pytest.mark.parametrize("alg", ["tsit5", "rodas5p"])
+def test_fast_mode_packed_pairs_and_one_per_thread_agree(dg, n, alg, monkeypatch):
+    """ragged launch sizes through both forms of the fast adaptive kernel (an odd count leaves the last packed pair half
+    empty): same saved times and return codes, values within 50 * reltol (99 % quantile) on the calm part of the sweep,
+    accepted-step counts within 4"""
+    p = lorenz_sweep(n, seed=17)
+    p[:, 1] = 1.0 + 11.0 * (p[:, 1] / 28.0)                      # rho in (1, 12): fixed points, no chaotic amplification
+    sv = np.arange(0, 6, dtype=f32)
+    kw = dict(dt=0.05, adaptive=True, abstol=1e-6, reltol=1e-5, saveat=sv, fp_mode="fast")
+    out = {}
+    for width, below in (("one", str(1 << 40)), ("two", "0")):
+        monkeypatch.setenv("DEGK_ADAPTIVE_W1_BELOW", below)
+        out[width] = gpu_solve(dg, "lorenz", alg, U0_LORENZ, p, [0, 5], **kw)
+    a, b = out["one"], out["two"]
+    assert np.array_equal(a["ts"], b["ts"]) and (a["retcode"] == 1).all() and (b["retcode"] == 1).all()
+    # (a few members of the sweep are sensitive -- the strict and fast builds differ by up to 2e-2 on them as well -- so
+    #  the gate is on quantiles: measured 2e-6 / 9e-5 at 50 / 99 % for Rodas5P, identical bits for Tsit5)
+    rel = (np.abs(a["us"] - b["us"]) / np.maximum(np.abs(b["us"]), 1.0)).max(axis=(1, 2))
+    assert np.quantile(rel, 0.5) < 1e-5 and np.quantile(rel, 0.99) < 50 * 1e-5 and rel.max() < 0.1, np.quantile(rel, [0.5, 0.99, 1.0])
+    assert np.abs(a["naccept"].astype(int) - b["naccept"].astype(int)).max() <= 4
 
 
 # ------------------------------------------------------------------------------------------

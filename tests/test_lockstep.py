@@ -125,6 +125,26 @@ def test_fast_build_packed_pairs_within_tolerance(dg):
     assert (np.abs(g["us"] - f["us"]) / scale).max() < 5e-4
 
 
+@pytest.mark.parametrize("n", [1, 33, 63, 64, 65, 2049])
+@pytest.mark.parametrize("layout", ["ref", "soa"])
+def test_fast_build_both_widths(dg, n, layout, monkeypatch):
+    """the fast Float32 build has the lock-step kernel with two trajectories per thread (packed pairs) and with one
+    (degk_api.cu picks by layout and launch size; DEGK_LOCKSTEP_W1_BELOW pins it): same rows, values within rounding"""
+    p = lorenz_sweep(n, seed=23)
+    out = {}
+    for width, below in (("one", str(1 << 40)), ("two", "0")):
+        monkeypatch.setenv("DEGK_LOCKSTEP_W1_BELOW", below)
+        out[width] = solve(dg, "tsit5", p, [0, 2.35], 0.05, engine="lockstep", fp_mode="fast", layout=layout)
+    a, b = out["one"], out["two"]
+    assert np.array_equal(a["ts"], b["ts"]) and np.array_equal(a["naccept"], b["naccept"])
+    assert (np.abs(a["us"] - b["us"]) / np.maximum(np.abs(b["us"]), 1.0)).max() < 5e-4
+    monkeypatch.delenv("DEGK_LOCKSTEP_W1_BELOW")
+    s = solve(dg, "tsit5", p, [0, 2.35], 0.05, engine="lockstep", fp_mode="strict", layout=layout)
+    assert np.array_equal(a["ts"], s["ts"])
+    # (47 steps of the chaotic members amplify the rounding difference between fused and un-fused arithmetic)
+    assert (np.abs(a["us"] - s["us"]) / np.maximum(np.abs(s["us"]), 1.0)).max() < 5e-3
+
+
 def test_large_launch_takes_it_by_default(dg):
     """engine="auto" switches to the lock-step kernel for launches that fill the GPU: identical strict results"""
     p = lorenz_sweep(200_000, seed=2)
