@@ -66,6 +66,19 @@ struct KArgs {
 };
 
 // ---- fused multiply-add that stays fused in both fp modes (reference: @muladd / muladd) ----
+// tableau coefficient `v`, entry `i` of the method's __constant__ table `tab` (gen_erk_*.cuh).  Default: the literal for
+// every element type.  With DEGK_COEF_TABLE 1 the Float64 instantiations read the table instead: a 64-bit literal costs
+// two UMOVs each time it is used (266 UMOV next to 235 DFMA in one Vern9 attempt), a table entry half an LDCU.128 --
+// 37 % fewer SASS instructions in the Vern9 Float64 kernels, but the FP64 pipe, not the issue slots, bounds them:
+// measured C3 Henon-Heiles +6.6 %, C3 Lorenz -2 %, lock-step Float64 +2 %, one-thread-per-trajectory Vern9 Float64
+// -12 %, so it stays off.
+#ifndef DEGK_COEF_TABLE
+#define DEGK_COEF_TABLE 0
+#endif
+template <class T> DEGK_DEV T coef_(const double* tab, int i, double v) { (void)tab; (void)i; return (T)v; }
+#if DEGK_COEF_TABLE
+template <> DEGK_DEV double coef_<double>(const double* tab, int i, double v) { (void)v; return tab[i]; }
+#endif
 DEGK_DEV float  fma_(float a, float b, float c)    { return fmaf(a, b, c); }
 DEGK_DEV double fma_(double a, double b, double c) { return fma(a, b, c); }
 
