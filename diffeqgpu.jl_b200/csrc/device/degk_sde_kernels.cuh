@@ -6,16 +6,14 @@
 // RNG.  The reference seeds a backend-dependent device RNG per thread (`Random.seed!(prob.seed)`,
 // gpu_em_perform_step.jl:8; degenerate on its CPU backend).  Here the stream is
 // counter based and therefore independent of launch geometry and of how an ensemble is sharded
-// over GPUs: normals for (global trajectory i, step j) = BoxMuller(Philox4x32-10(key = seed,
-// counter = (j, block, i_lo, i_hi))).  Seed and trajectory index occupy different Philox words, so two seeds
+// over GPUs: normal q of global trajectory i (q counts the normals of the whole run: step j with m noise terms uses
+// q = j m ... j m + m - 1) is element q & 3 of BoxMuller(Philox4x32-10(key = seed, counter = (q >> 2, i_lo, i_hi)))
+// -- see normals_of_block.  Seed and trajectory index occupy different Philox words, so two seeds
 // never share a stream (with key = seed ^ i, seeds s and s ^ d would only permute the paths of an ensemble).
 // The u32 stream is bit-identical to the oracle's.
 #pragma once
 #include "degk_common.cuh"
 
-#ifndef DEGK_SDE_PAIR
-#define DEGK_SDE_PAIR 1      // end-point runs: two steps per loop trip (see sde_solve_body)
-#endif
 #ifndef DEGK_SDE_MINBLOCKS
 #define DEGK_SDE_MINBLOCKS 1
 #endif
@@ -67,15 +65,45 @@ DEGK_DEV void box_muller(u32 a, u32 b, double& z0, double& z1) {
     z1 = r * s;
 }
 
+// The normals of a trajectory form ONE sequence over the whole run: step j (0-based) with m noise terms consumes normals
+// q = j m ... j m + m - 1, and normal q is element q & 3 of Philox block q >> 2 (elements (0, 1) and (2, 3) are the two
+// Box-Muller pairs of the block's four words).  No word of a block is thrown away: m = 3 (BASELINE config 5) needs three
+// blocks per four steps instead of four, m = 1 one instead of four.
+template <class T>
+DEGK_DEV void normals_of_block(u32 k0, u32 k1, u32 g0, u32 g1, u64 blk, T (&zz)[4]) {
+    u32 r[4];
+    philox4x32_10((u32)blk, (u32)(blk >> 32), g0, g1, k0, k1, r);
+    box_muller(r[0], r[1], zz[0], zz[1]);
+    box_muller(r[2], r[3], zz[2], zz[3]);
+}
+// steps per group / blocks per group: the shortest run of steps that consumes whole blocks
+template <int MM> struct NormalGroup {
+    static constexpr int G = (MM % 4 == 0) ? 1 : (MM % 2 == 0 ? 2 : 4);
+    static constexpr int NB = G * MM / 4;
+};
+// all normals of steps group*G ... group*G + G - 1 (z[g * MM + c]); the NB Philox chains are independent of each other
+// and of the state, so they are in flight together
+template <class T, int MM>
+DEGK_DEV void normals_for_group(u32 k0, u32 k1, u32 g0, u32 g1, u64 group, T (&z)[NormalGroup<MM>::G * MM]) {
+    constexpr int NB = NormalGroup<MM>::NB;
+    const u64 b0 = group * (u64)NB;
+    DEGK_UNROLL for (int b = 0; b < NB; ++b) {
+        T zz[4];
+        normals_of_block<T>(k0, k1, g0, g1, b0 + (u64)b, zz);
+        DEGK_UNROLL for (int q = 0; q < 4; ++q) z[4 * b + q] = zz[q];
+    }
+}
+// the normals of one step wherever it lies in the sequence (the steps behind the last whole group)
 template <class T, int MM>
 DEGK_DEV void normals_for_step(u32 k0, u32 k1, u32 g0, u32 g1, u32 step, T (&z)[MM]) {
-    DEGK_UNROLL for (int b = 0; 4 * b < MM; ++b) {
-        u32 r[4];
-        philox4x32_10(step, (u32)b, g0, g1, k0, k1, r);
-        T zz[4];
-        box_muller(r[0], r[1], zz[0], zz[1]);
-        if (4 * b + 2 < MM) box_muller(r[2], r[3], zz[2], zz[3]);
-        DEGK_UNROLL for (int q = 0; q < 4; ++q) if (4 * b + q < MM) z[4 * b + q] = zz[q];
+    const u64 q0 = (u64)step * (u64)MM;
+    u64 have = ~(u64)0;
+    T zz[4] = {(T)0, (T)0, (T)0, (T)0};
+    DEGK_UNROLL for (int c = 0; c < MM; ++c) {
+        const u64 q = q0 + (u64)c, blk = q >> 2;
+        if (blk != have) { normals_of_block<T>(k0, k1, g0, g1, blk, zz); have = blk; }
+        const u32 e = (u32)q & 3u;
+        z[c] = e == 0 ? zz[0] : (e == 1 ? zz[1] : (e == 2 ? zz[2] : zz[3]));
     }
 }
 
@@ -188,29 +216,8 @@ DEGK_DEV void sde_solve_body(const KArgs& a) {
         }
         t = t + dt;
     };
-    auto advance = [&](i64 j) {
-        T z[MM];
-        normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 2), z);
-        advance_z(z);
-    };
-    if (!has_saveat && !a.save_everystep) {
-        // endpoints only (ensemble moments, BASELINE config 5): nothing to test or store per step -- the general loop
-        // below spends ~25 of its 129 instructions per step on the save options.  Two steps per trip: the normals do
-        // not depend on the state, so both Philox chains (ten serial rounds each) are in flight together.
-        i64 j = 2;
-#if DEGK_SDE_PAIR
-        for (; j + 1 <= nst; j += 2) {
-            T z0[MM], z1[MM];
-            normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 2), z0);
-            normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 1), z1);
-            advance_z(z0);
-            advance_z(z1);
-        }
-#endif
-        for (; j <= nst; ++j) advance(j);
-    }
-    for (i64 j = 2; j <= nst && (has_saveat || a.save_everystep); ++j) {
-        advance(j);
+    // what follows step j (1-based row index j - 1) when rows are kept
+    auto after_step = [&](i64 j) {
         if (!has_saveat) {
             if (a.save_everystep) {
                 if (active) { store_u<T, N>(a, traj, j - 1, u); store_t<T>(a, traj, j - 1, t); }
@@ -228,7 +235,35 @@ DEGK_DEV void sde_solve_body(const KArgs& a) {
                 ++cur;
             }
         }
+    };
+    // Steps run in groups that consume whole Philox blocks (NormalGroup: four steps and three blocks for m = 3); the
+    // steps behind the last whole group take their normals one step at a time.  Two copies of the loop: end points only
+    // (ensemble moments, BASELINE config 5) has nothing to test or store per step -- the save options cost ~25 of the
+    // ~130 instructions of a step.
+    constexpr int G = NormalGroup<MM>::G;
+    const bool keep_rows = has_saveat || a.save_everystep;
+    i64 j = 2;
+#define DEGK_SDE_GROUPS(AFTER)                                                                     \
+    for (; j + (G - 1) <= nst; j += G) {                                                           \
+        T zall[G * MM];                                                                            \
+        normals_for_group<T, MM>(k0, k1, g0, g1, (u64)(j - 2) / (u64)G, zall);                     \
+        DEGK_UNROLL for (int g = 0; g < G; ++g) {                                                  \
+            T z[MM];                                                                               \
+            DEGK_UNROLL for (int c = 0; c < MM; ++c) z[c] = zall[g * MM + c];                      \
+            advance_z(z);                                                                          \
+            AFTER(j + g);                                                                          \
+        }                                                                                          \
+    }                                                                                              \
+    for (; j <= nst; ++j) {                                                                        \
+        T z[MM];                                                                                   \
+        normals_for_step<T, MM>(k0, k1, g0, g1, (u32)(j - 2), z);                                  \
+        advance_z(z);                                                                              \
+        AFTER(j);                                                                                  \
     }
+#define DEGK_SDE_NOTHING(jj) ((void)0)
+    if (keep_rows) { DEGK_SDE_GROUPS(after_step) } else { DEGK_SDE_GROUPS(DEGK_SDE_NOTHING) }
+#undef DEGK_SDE_GROUPS
+#undef DEGK_SDE_NOTHING
     if (!has_saveat && !a.save_everystep) {
         if (active) { store_u<T, N>(a, traj, 1, u); store_t<T>(a, traj, 1, t); }
         if (red) reduce_row<T, N>(a, 1, u, active);

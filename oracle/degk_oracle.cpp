@@ -286,8 +286,8 @@ inline void model_G(int id, T (*G)[MAXN], const T* u, const T* p, T t) {
 }
 
 // =====================================================================================
-// Philox4x32-10 (Salmon et al. 2011), key = (seed_lo ^ traj_lo, seed_hi ^ traj_hi),
-// counter = (step, draw_block, 0, 0).  Normals by Box-Muller on (u32 -> (0,1]) pairs.
+// Philox4x32-10 (Salmon et al. 2011), key = seed, counter = (block_lo, block_hi, traj_lo, traj_hi) -- see
+// normals_for_step.  Normals by Box-Muller on (u32 -> (0,1]) pairs.
 // The reference's RNG is backend-dependent and degenerate on its CPU backend, so
 // this stream is OUR definition; oracle and kernel must agree bit-for-bit on the u32s.
 // =====================================================================================
@@ -321,19 +321,26 @@ inline void box_muller(uint32_t a, uint32_t b, T& z0, T& z1) {
     z1 = r * std::sin(th);
 }
 
-// normals for (traj, step): draws m normals; block b covers normals 4b..4b+3
+// normals for (traj, step): the normals of a trajectory form one sequence over the whole run -- step j (0-based) with
+// m noise terms uses q = j m ... j m + m - 1, and normal q is element q & 3 of Philox block q >> 2 (elements (0, 1) and
+// (2, 3) are the two Box-Muller pairs of the block's four words), so no word of a block is thrown away
 template <class T>
 inline void normals_for_step(uint64_t seed, uint64_t traj, uint32_t step, int m, T* z) {
-    // seed and trajectory index live in different Philox words (key = seed, counter = (step, block, traj)):
+    // seed and trajectory index live in different Philox words (key = seed, counter = (block_lo, block_hi, traj)):
     // two seeds never share a stream, whatever the trajectory indices are
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int b = 0; 4 * b < m; ++b) {
-        uint32_t r[4];
-        philox4x32_10(step, (uint32_t)b, (uint32_t)traj, (uint32_t)(traj >> 32), k0, k1, r);
-        T zz[4];
-        box_muller<T>(r[0], r[1], zz[0], zz[1]);
-        box_muller<T>(r[2], r[3], zz[2], zz[3]);
-        for (int q = 0; q < 4 && 4 * b + q < m; ++q) z[4 * b + q] = zz[q];
+    uint64_t have = ~(uint64_t)0;
+    T zz[4] = {0, 0, 0, 0};
+    for (int c = 0; c < m; ++c) {
+        const uint64_t q = (uint64_t)step * (uint64_t)m + (uint64_t)c, blk = q >> 2;
+        if (blk != have) {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)traj, (uint32_t)(traj >> 32), k0, k1, r);
+            box_muller<T>(r[0], r[1], zz[0], zz[1]);
+            box_muller<T>(r[2], r[3], zz[2], zz[3]);
+            have = blk;
+        }
+        z[c] = zz[q & 3];
     }
 }
 
