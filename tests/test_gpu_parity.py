@@ -563,6 +563,26 @@ def test_c5_model_lorenz_additive_em(dg, oracle, fp):
     assert np.abs(m_g - m_r).max() < 1e-3 * max(1.0, np.abs(m_r).max()) and np.abs(v_g - v_r).max() < 1e-2 * max(1.0, v_r.max())
 
 
+@pytest.mark.parametrize("nsteps", [1, 2, 3, 5, 6, 7, 9, 13])
+def test_sde_whole_block_groups_and_the_steps_behind_them(dg, oracle, nsteps):
+    """The kernel draws normals in groups of steps that consume whole Philox blocks (three noise terms: four steps and
+    three blocks; one: four steps and one block; four: every step) and the steps behind the last group one at a time:
+    step counts around the group size, every-step saves, saveat and end points, against the oracle path by path."""
+    dt, tf = 1 / 64, nsteps / 64
+    for model, name, u0, p in ((dg.models.gbm, "gbm", np.full((257, 3), 0.1, f32), [1.5, 0.2]),
+                               (dg.models.scalar_sde, "scalar_sde", np.full((257, 1), 0.5, f32), [1.0, 0.5]),
+                               (dg.models.gbm_nd, "gbm_nd", np.full((257, 2), 0.1, f32), [1.5, 0.1])):
+        for kw in (dict(save_everystep=True), dict(save_everystep=False), dict(saveat=np.linspace(0, tf, 4).astype(f32))):
+            g = sde_solve(dg, model, "em", u0, p, [0, tf], dt=dt, seed=77, **kw)
+            okw = dict(kw, length=g["us"].shape[1]) if kw.get("save_everystep") and "saveat" not in kw else kw
+            r = oracle.solve(name, "em", u0, p, [0, tf], dt=dt, seed=77, **okw)
+            assert np.array_equal(g["ts"], r["ts"]), (name, kw)
+            assert np.abs(g["us"] - r["us"]).max() < 1e-4 * max(1.0, np.abs(r["us"]).max()), (name, kw)
+    g = sde_solve(dg, dg.models.gbm, "siea", np.full((257, 3), 0.1, f32), [1.5, 0.2], [0, tf], dt=dt, seed=77)
+    r = oracle.solve("gbm", "siea", np.full((257, 3), 0.1, f32), [1.5, 0.2], [0, tf], dt=dt, seed=77, length=g["us"].shape[1])
+    assert np.array_equal(g["ts"], r["ts"]) and np.abs(g["us"] - r["us"]).max() < 1e-4 * max(1.0, np.abs(r["us"]).max())
+
+
 @pytest.mark.parametrize("alg", ["em", "siea"])
 def test_sde_fast_mode_matches_oracle(dg, oracle, alg):
     """fast build of the SDE kernels (the C5 throughput numbers use it): same Philox words, MUFU log / sincos in
