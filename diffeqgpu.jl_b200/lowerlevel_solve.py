@@ -10,6 +10,7 @@ is replaced by `degk_solve` (include/degk.h).  Returns `(ts, us)` still on the d
 ts (N, len) and us (N, len, n) torch tensors whose memory is exactly the reference's
 column-major (len x N) arrays.
 """
+import contextlib
 import ctypes as C
 import math
 
@@ -118,6 +119,8 @@ def get_program(prob, alg, fp_mode="strict", device=None, callback=None, events=
             raise NotImplementedError("tstops / callbacks are lowered for ODE problems only")
         sf, f = prob.f, prob.f.f
         key = ("sde", _model_key(f), sf.g, sf.noise, sf.n_noise, alg.alg_id, dtype, fp_mode)
+        if key in ctx._programs:
+            return ctx._programs[key]
         kind = {"diagonal": _lib.NOISE_DIAGONAL, "general": _lib.NOISE_GENERAL}[sf.noise]
         desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, noise_src=sf.g, n_state=f.n_state, n_param=f.n_param,
                               n_noise=sf.n_noise, noise_kind=kind, dtype=dtype, alg=alg.alg_id,
@@ -126,6 +129,8 @@ def get_program(prob, alg, fp_mode="strict", device=None, callback=None, events=
         f = prob.f
         jac_mode, jac_src = _jac_mode(f, alg)
         key = ("ode", _model_key(f), alg.alg_id, dtype, fp_mode, events, cbs.key(), cbs.ckey(), jac_mode)
+        if key in ctx._programs:               # (the descriptor is only needed to build)
+            return ctx._programs[key]
         desc = _lib.make_desc(builtin=f.builtin, rhs_src=f.rhs, jac_src=jac_src, tgrad_src=f.tgrad if jac_mode == 0 else None,
                               n_state=f.n_state, n_param=f.n_param, dtype=dtype, alg=alg.alg_id,
                               fp_mode=FP_MODES[fp_mode], force_jit=f.force_jit, events=events,
@@ -151,8 +156,14 @@ def _launch(probs, prob, alg, *, dt, adaptive, abstol, reltol, saveat, save_ever
     tdt = torch.float32 if prob.dtype == np.float32 else torch.float64
     # allocations and the small H2D copies below are ordered on the stream the kernel is launched on (the caller's
     # `stream` when given): torch's caching allocator ties a block to the stream it was allocated on
+    # (the context managers cost ~40 us of Python per call, more than a small ensemble's kernel: they are entered only
+    #  when the launch stream / device differ from the current ones)
     launch_stream = torch.cuda.current_stream(dev) if stream is None else torch.cuda.ExternalStream(int(stream), device=dev)
-    with torch.cuda.device(dev), torch.cuda.stream(launch_stream):
+    with contextlib.ExitStack() as ctx_stack:
+        if dev.index is not None and torch.cuda.current_device() != dev.index:
+            ctx_stack.enter_context(torch.cuda.device(dev))
+        if stream is not None:
+            ctx_stack.enter_context(torch.cuda.stream(launch_stream))
         # allocate(backend, T, (len, N)) -- lowerlevel_solve.jl:81-83 / 317-323.  ts needs no
         # fill!(ts, t0): the kernel writes t0 into every row it does not reach.
         if layout == "ref":
@@ -248,9 +259,12 @@ class SolvePlan:
             self.reduce.zero_()
 
     def __call__(self):
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            self._reset()
+        if self.stats is None and self.reduce is None:        # nothing for torch to do: one FFI call
             self._launch()
+        else:
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                self._reset()
+                self._launch()
         return self.result()
 
     def capture(self, launches=1):
