@@ -382,7 +382,9 @@ DEGK_DEV void ode_asolve_body(const KArgs& a) {
                         DEGK_UNROLL for (int c = 0; c < N; ++c) u[c] = unew[c];
                         t = tnew;
                         h = dtnew;
-                        if (!finite_(tnew) || !finite_(dtnew)) rc = RC_UNSTABLE;
+                        // (a NaN dtnew is attempted like any other step, as in the reference: that attempt is accepted
+                        //  -- NaN > 1 is false --, tnew becomes NaN and the `!(tnew < tf)` branch above ends the
+                        //  trajectory with the NaN end point and Unstable)
                     }
                 }
                 if (rc == RC_DEFAULT && ++iters >= a.max_iters) rc = RC_MAXITERS;

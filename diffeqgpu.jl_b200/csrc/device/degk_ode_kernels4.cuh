@@ -213,6 +213,12 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
     const u32 max_it = a.max_iters > 0x3fffffffLL ? 0x3fffffffu : (u32)a.max_iters;
     const T kInf = (T)__longlong_as_double(0x7ff0000000000000LL);   // +inf: "no further save point"
     const T dtmin = MethodS::dtmin();
+    // A slot integrates while its step is not below dtmin.  Strict build: exactly the reference's `dt < dtmin` test, so a
+    // NaN step (the controller of a trajectory that went non-finite) is still attempted: that attempt is accepted (NaN
+    // > 1 is false), t becomes NaN, `while t < tf` ends and the end-point row / retcode come from the NaN state -- as
+    // in the reference and the oracle.  Fast build: a NaN step is not live (its slots stop by themselves through
+    // h < dtmin, which a NaN never satisfies).
+    auto is_live = [&](T hh) { return FAST ? (hh >= dtmin) : !(hh < dtmin); };
     const T kDead = (T)-1;                   // h of a slot that is not integrating
 
     // fast controller constants in the L = log2(N * EEst^2) representation
@@ -392,12 +398,12 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
             if (__any_sync(0xffffffffu, qaddr >= qtrig)) flush_saves(false);
             // maximum number of attempts reached: park the slot, the retire path reports MaxIters
             DEGK_UNROLL for (int s = 0; s < W; ++s)
-                if (natt[s] >= max_it && h[s] >= dtmin) h[s] = kDead;
+                if (natt[s] >= max_it && is_live(h[s])) h[s] = kDead;
             for (;;) {
                 // slot states: integrating (h >= dtmin) / stopped, waiting to retire / free
                 u32 havem = 0, donem = 0;
                 DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                    const bool hv = h[s] >= dtmin;
+                    const bool hv = is_live(h[s]);
                     havem |= (u32)hv << s;
                     donem |= (u32)(!hv & (traj[s] >= 0)) << s;
                 }
@@ -426,7 +432,7 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
                         if ((donem >> s) & 1u) {
                             int rc = RC_SUCCESS;
                             const u32 natt_ = natt[s];
-                            if (t[s] >= tf[s]) {
+                            if (!(t[s] < tf[s])) {                   // reached tf -- or t is NaN (`while t < tf` ended)
                                 T uf[N];
                                 DEGK_UNROLL for (int c = 0; c < N; ++c) uf[c] = PO::get(u[c], s);
                                 if (!has_saveat && !a.save_everystep) {  // kernels.jl:139-142
@@ -497,7 +503,7 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
                 // anything integrating now?
                 bool mine_live = false, mine_wait = false;
                 DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                    const bool hv = h[s] >= dtmin;
+                    const bool hv = is_live(h[s]);
                     mine_live |= hv;
                     mine_wait |= !hv & (traj[s] >= 0);
                 }
@@ -593,7 +599,7 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
             }
             const T tn = land ? tf[s] : tsum_[s];
             const T hn = rej[s] ? hf_[s] : hacc;
-            const bool live = h[s] >= dtmin;                     // dead slots carry h < dtmin
+            const bool live = is_live(h[s]);                     // dead slots carry h < dtmin
             const bool ok = live & solved;                       // W factorised
             const bool accept = ok & !rej[s];
             inc_if(ok, natt[s]);

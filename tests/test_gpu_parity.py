@@ -368,6 +368,33 @@ def test_c4_fast_accuracy_against_float64(dg):
     assert abs(err["fast"][3] - err["strict"][3]) < 0.05 * err["strict"][3], err
 
 
+@pytest.mark.parametrize("engine", ["auto", "v1"])
+def test_non_finite_trajectory_ends_like_the_reference_loop(dg, oracle, engine):
+    """A trajectory whose controller produces a NaN step (Rodas5P on Robertson at reltol 3e-3, found by
+    tools/fuzz_parity.py): the reference attempts the NaN step, accepts it (`EEst > 1` is false for NaN), t becomes NaN
+    and `while t < tf` ends -- the end-point row holds NaN, the accepted-step count includes that step, the return code
+    is Unstable.  The strict build does exactly that, in both adaptive kernels."""
+    import torch
+    p = np.array([[5.8925923e-02, 4.1694392e+07, 8.2660371e+03], [0.04, 3e7, 1e4]], f32).repeat(40, axis=0)
+    kw = dict(dt=0.003535440943764088, adaptive=True, abstol=2.889140466915445e-07, reltol=0.0033294803945065426)
+    for extra in (dict(save_everystep=False), dict(saveat=np.array([0.09679443, 0.23163624, 2.137411], f32))):
+        r = oracle.solve("rober", "rodas5p", [1, 0, 0], p, [0.0, 4.364859095929368], **kw, **extra)
+        assert (r["retcode"][:40] == 3).all() and (r["naccept"][:40] == 2).all() and (r["retcode"][40:] == 1).all()
+        prob = dg.ODEProblem(dg.models.rober, np.array([1, 0, 0], f32), (0.0, 4.364859095929368), p[0])
+        probs = dg.ProblemBatch.from_arrays(prob, p=p, device="cuda:0")
+        ts, us, st = dg.vectorized_asolve(probs, prob, dg.GPURodas5P(), dt=f32(kw["dt"]), abstol=f32(kw["abstol"]), reltol=f32(kw["reltol"]),
+                                          stats=True, engine=engine, **extra)
+        torch.cuda.synchronize()
+        ts, us = ts.cpu().numpy(), us.cpu().numpy()
+        for k in ("naccept", "nreject", "retcode"):
+            assert np.array_equal(st[k].cpu().numpy(), r[k]), (k, extra.keys())
+        assert np.array_equal(ts, r["ts"], equal_nan=True)
+        written = ~((ts == 0) & (np.arange(ts.shape[1])[None, :] > 0))          # unreached saveat rows keep t0, `us` is unwritten there
+        if "saveat" in extra:
+            written &= r["retcode"][:, None] == 1
+        assert np.array_equal(us[written], r["us"][written], equal_nan=True)
+
+
 # ------------------------------------------------------------------------------------------
 # JIT (NVRTC) path == ahead-of-time path, and a model that only exists as source
 # ------------------------------------------------------------------------------------------
