@@ -32,6 +32,9 @@ for it in range(cases):
     else:
         model, alg = "lorenz", str(rng.choice(["tsit5", "tsit5", "vern7", "vern9"]))
         u0, p = T.U0_LORENZ, lorenz_sweep(n, seed=int(rng.integers(1 << 30)))
+        if rng.random() < 0.25:                  # four states, no parameters, per-trajectory initial values
+            from cases import henon_heiles_u0
+            model, u0, p = "henon_heiles", henon_heiles_u0(n, seed=int(rng.integers(1 << 30))).astype(f32), None
         t0 = float(rng.choice([0.0, 0.0, 0.37, 1.0]))
         tf = t0 + float(rng.choice([0.05, 0.5, 2.0, 5.0, 10.0, 17.3]))
         dt0 = float(rng.choice([1e-3, 0.01, 0.1, 0.5, 30.0]))
@@ -57,8 +60,12 @@ for it in range(cases):
     sched = str(rng.choice(["auto", "queue", "static"])) if kw.get("adaptive") else "auto"
     desc = dict(it=it, n=n, model=model, alg=alg, tspan=[t0, tf], mode=mode, sched=sched,
                 **{k: (v if not isinstance(v, np.ndarray) else f"{len(v)} points") for k, v in kw.items()})
+    layout = str(rng.choice(["ref", "ref", "soa"]))
+    desc["layout"] = layout
     try:
-        g = T.gpu_solve(dg, model, alg, u0, p, [t0, tf], schedule=sched, **kw)
+        g = T.gpu_solve(dg, model, alg, u0, p, [t0, tf], schedule=sched, layout=layout, **kw)
+        if layout == "soa":                      # (rows, n, N) / (rows, N) -> the reference's (N, rows, n) / (N, rows)
+            g["us"], g["ts"] = g["us"].transpose(2, 0, 1), g["ts"].T
         okw = dict(kw)
         if mode == "fixed":
             okw["length"] = g["us"].shape[1]
