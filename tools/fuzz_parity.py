@@ -20,6 +20,7 @@ f32 = np.float32
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20261018)
 bad = 0
+seen = {}
 for it in range(cases):
     n = int(rng.choice([1, 2, 31, 32, 33, 63, 65, 127, 129, 255, 257, 1000, 2049, 4097]))
     stiff = rng.random() < 0.25
@@ -61,8 +62,30 @@ for it in range(cases):
     desc = dict(it=it, n=n, model=model, alg=alg, tspan=[t0, tf], mode=mode, sched=sched,
                 **{k: (v if not isinstance(v, np.ndarray) else f"{len(v)} points") for k, v in kw.items()})
     layout = str(rng.choice(["ref", "ref", "soa"]))
-    desc["layout"] = layout
+    ragged = model == "lorenz" and mode != "fixed" and rng.random() < 0.3     # per-trajectory u0 / p / tspan arrays
+    desc["layout"] = layout if not ragged else "ref"
+    desc["ragged"] = bool(ragged)
+    for key in (model, alg, mode, "ragged" if ragged else desc["layout"]):
+        seen[key] = seen.get(key, 0) + 1
     try:
+        if ragged:
+            u0a = (rng.standard_normal((n, 3)) * 2).astype(f32)
+            t0a = rng.choice([t0, t0 + 0.25], n)
+            tspan_a = np.stack([t0a, t0a + rng.uniform(0.2, max(0.3, tf - t0), n)], 1).astype(f32)
+            akw = {k: v for k, v in kw.items()}
+            g = T.gpu_solve_arrays(dg, alg, u0a, p, tspan_a, **akw)
+            r = oracle.solve(model, alg, u0a, p, tspan_a, **akw)
+            t0col = tspan_a[:, :1]
+            unwritten = (g["ts"] == t0col)
+            unwritten[:, 0] &= not (mode == "endpoints" or ("saveat" in kw and False))
+            if "saveat" in kw:
+                unwritten[:, 0] = (g["ts"][:, 0] == t0col[:, 0]) & (kw["saveat"][0] != t0col[:, 0])
+            for k in ("ts", "naccept", "nreject", "retcode"):
+                assert np.array_equal(g[k], r[k], equal_nan=True), f"{k} differs " + json.dumps(desc)
+            gu, ru = g["us"].copy(), r["us"].copy()
+            gu[unwritten] = 0; ru[unwritten] = 0
+            assert np.array_equal(gu, ru, equal_nan=True), "us differs (max |d| = %g) " % np.nanmax(np.abs(gu.astype(np.float64) - ru.astype(np.float64))) + json.dumps(desc)
+            continue
         g = T.gpu_solve(dg, model, alg, u0, p, [t0, tf], schedule=sched, layout=layout, **kw)
         if layout == "soa":                      # (rows, n, N) / (rows, N) -> the reference's (N, rows, n) / (N, rows)
             g["us"], g["ts"] = g["us"].transpose(2, 0, 1), g["ts"].T
@@ -86,5 +109,5 @@ for it in range(cases):
     except Exception as e:                       # refused configurations must be refused by both sides
         print("ERROR", type(e).__name__, str(e)[:200], json.dumps(desc), flush=True)
         bad += 1
-print(json.dumps(dict(cases=cases, mismatches=bad)))
+print(json.dumps(dict(cases=cases, mismatches=bad, seen=seen)))
 sys.exit(1 if bad else 0)
