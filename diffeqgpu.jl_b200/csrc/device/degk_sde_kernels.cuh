@@ -39,15 +39,19 @@ DEGK_DEV float  u01_(u32 x, float)  { return (float)((x >> 8) + 1u) * 5.96046447
 DEGK_DEV double u01_(u32 x, double) { return ((double)x + 1.0) * 2.3283064365386963e-10; }
 
 DEGK_DEV void box_muller(u32 a, u32 b, float& z0, float& z1) {
-    const float u1 = u01_(a, 0.f), u2 = u01_(b, 0.f);
-    const float th = 6.283185307179586476925286766559f * u2;
     float s, c;
 #if DEGK_STRICT
+    const float u1 = u01_(a, 0.f), u2 = u01_(b, 0.f);
+    const float th = 6.283185307179586476925286766559f * u2;
     const float r = sqrtf(-2.0f * logf(u1));
     sincosf(th, &s, &c);
 #else
     // u1 is in [2^-24, 1], never subnormal: the MUFU logarithm and square root as they are (lg2 / sqrt.approx.ftz),
-    // without the range guards and Newton step of __logf / sqrtf (12 instructions and two branches per pair)
+    // without the range guards and Newton step of __logf / sqrtf (12 instructions and two branches per pair); the angle
+    // 2 pi u2 = n2 (2 pi 2^-24) is one multiply of the integer (one rounding instead of two).  (The same folding for
+    // the logarithm, -2 ln2 (lg2 n1 - 24), would cancel near u1 = 1 and is not done.)
+    const float u1 = u01_(a, 0.f);
+    const float th = 3.7450702829239286e-7f * (float)((b >> 8) + 1u);
     float l2, r;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));      // sqrt(-2 ln u1)
