@@ -16,6 +16,7 @@ from cases import lorenz_sweep, rober_sweep  # noqa: E402
 from oracle import oracle  # noqa: E402
 import test_gpu_parity as T  # noqa: E402
 
+T.ALGS.update(kvaerno3="GPUKvaerno3", kvaerno5="GPUKvaerno5")
 f32 = np.float32
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20261018)
@@ -25,7 +26,7 @@ for it in range(cases):
     n = int(rng.choice([1, 2, 31, 32, 33, 63, 65, 127, 129, 255, 257, 1000, 2049, 4097]))
     stiff = rng.random() < 0.25
     if stiff:
-        model, alg = "rober", str(rng.choice(["rodas5p", "rodas4", "rosenbrock23"]))
+        model, alg = "rober", str(rng.choice(["rodas5p", "rodas4", "rosenbrock23", "kvaerno3", "kvaerno5"]))
         u0, p = [1, 0, 0], rober_sweep(n, seed=int(rng.integers(1 << 30)))
         t0, tf = 0.0, float(10 ** rng.uniform(-1, 3))
         dt0 = float(10 ** rng.uniform(-5, -2))
