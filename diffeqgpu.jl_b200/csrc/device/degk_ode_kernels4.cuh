@@ -537,7 +537,7 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
                 accf = fmaf(v, v, accf);
             }
             const float Lf = log2_(accf);                            // log2(N * EEst^2)
-            rej[0] = accf > (float)N;                                // EEst > 1
+            rej[0] = !(accf <= (float)N);                            // EEst > 1 -- or NaN: see the packed branch below
             const float lqe = rej[0] ? (float)lqZero : (float)lq[0];
             const float ex = vclamp(fmaf(-(float)b1h, Lf, fmaf((float)b2h, lqe, (float)k0)), (float)exLo, (float)exHi);
             hf_[0] = h[0] * (T)exp2_(ex);                            // dt * fac
@@ -555,7 +555,11 @@ DEGK_DEV void ode_asolve4_body(const KArgs& a, unsigned char* smem_raw) {
             const V L = vlog2(accn);                                 // log2(N * EEst^2)
             T lqe[W];
             DEGK_UNROLL for (int s = 0; s < W; ++s) {
-                rej[s] = PO::get(accn, s) > (T)N;                    // EEst > 1
+                // EEst > 1.  A NaN estimate (an attempt that overflowed: a start step far beyond the span, say, where the
+                // fused arithmetic of this build meets inf - inf sooner than the reference's) is REJECTED here and the
+                // step shrinks by the largest factor (the clamp below maps NaN to its lower bound); the reference, and
+                // the strict build, accept it (`NaN > 1` is false) and lose the trajectory
+                rej[s] = !(PO::get(accn, s) <= (T)N);
                 lqe[s] = rej[s] ? lqZero : lq[s];
             }
             const V ex = vclamp(fma_(V(-b1h), L, fma_(V(b2h), PO::make(lqe), V(k0))), exLo, exHi);
