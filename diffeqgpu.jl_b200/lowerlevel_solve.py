@@ -274,7 +274,9 @@ class SolvePlan:
         side = torch.cuda.Stream(self.device)
         side.wait_stream(self.stream)
         saved = self.stream
-        with torch.cuda.device(self.device), torch.cuda.graph(g, stream=side):
+        # (thread-local capture mode: other threads of the process -- an NCCL watchdog, a data loader -- may go on
+        #  calling the CUDA runtime while this one captures)
+        with torch.cuda.device(self.device), torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
             self.stream = torch.cuda.current_stream(self.device)
             for _ in range(int(launches)):
                 self._reset()
