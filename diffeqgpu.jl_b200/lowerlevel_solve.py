@@ -298,8 +298,9 @@ def vectorized_solve(probs, prob, alg, *, dt, saveat=None, save_everystep=True, 
     """Fixed-step batched solve; returns (ts, us) on the device (add `stats=True` for
     per-trajectory retcode/naccept/nreject and totals, which the reference does not have).
     `prepare=True` returns a `SolvePlan` instead of launching (re-launch with `plan()`).
-    `engine`: "auto" (the lock-step kernel for large launches with one tspan, every-step saves and an explicit RK
-    stepper, else one thread per trajectory), "lockstep" (whenever its preconditions hold), "v1" (never)."""
+    `engine`: "auto" (the lock-step kernel for launches with one tspan, every-step saves and an explicit RK
+    stepper, else one thread per trajectory), "lockstep" (the same, also where "auto" would not stage the reference
+    layout), "v1" (never)."""
     if not isinstance(alg, GPUODEAlgorithm):
         raise TypeError("alg must be a GPUODEAlgorithm / GPUSDEAlgorithm")
     is_sde = isinstance(prob, SDEProblem)

@@ -91,13 +91,14 @@ typedef enum {
     DEGK_RC_INIT_FAILURE = 7      /* DAE initialisation did not converge (dae_init; kernels.jl:63-70, 143-150) */
 } degk_retcode;
 
-/* DEGK_ENGINE_AUTO picks the second-generation adaptive kernel (batched deferred saves, two
- * trajectories per thread in FFMA2 register pairs for Float32 fast mode) when the program has
- * one, and for fixed-dt runs the lock-step kernel (uniform tspan and dt, every-step saves, explicit
- * RK stepper; two trajectories per thread in the Float32 fast mode) when the launch is large enough
- * to fill the GPU with it; DEGK_ENGINE_V1 forces the first-generation kernels (one thread per
+/* DEGK_ENGINE_AUTO picks the persistent adaptive kernel (batched deferred saves) when the program has
+ * one, and for fixed-dt runs the lock-step kernel whenever its preconditions hold (one tspan and dt for
+ * the launch, every-step saves, explicit RK stepper; a state too large for the staged flush of the
+ * reference layout keeps it only for launches that do not fill the GPU).  In the Float32 fast mode both
+ * carry two trajectories per thread in FFMA2 register pairs for launches that fill the GPU and one per
+ * thread below (degk_api.cu::launch); DEGK_ENGINE_V1 forces the first-generation kernels (one thread per
  * trajectory; kept for A/B measurements); DEGK_ENGINE_LOCKSTEP takes the lock-step kernel whenever
- * its preconditions hold, whatever the launch size. */
+ * its preconditions hold, whatever the layout and size. */
 typedef enum { DEGK_ENGINE_AUTO = 0, DEGK_ENGINE_V1 = 1, DEGK_ENGINE_LOCKSTEP = 2 } degk_engine;
 
 typedef enum { DEGK_NOISE_NONE = 0, DEGK_NOISE_DIAGONAL = 1, DEGK_NOISE_GENERAL = 2 } degk_noise;
