@@ -185,3 +185,33 @@ def test_sde_seeds_are_independent_streams():
     assert len(np.intersect1d(a, b)) == 0
     # trajectory i of seed 0 is not trajectory i ^ 1 of seed 1 any more
     assert not np.array_equal(a[np.arange(n) ^ 1], b)
+
+
+def test_normals_form_one_sequence_per_trajectory():
+    """The stream definition (oracle normals_for_step, kernel normals_of_block): normal q of a trajectory is element
+    q & 3 of the Box-Muller pairs of Philox block q >> 2 with key = seed and counter (block, trajectory), whatever the
+    number of noise terms per step -- so m = 1, 2, 3, 4 read the same sequence, no word of a block is skipped, and the
+    normals are Box-Muller of the raw Philox words."""
+    import ctypes
+    lib = oracle.lib()
+    seed, traj = 0x1234567890ABCDEF, 4097
+    def seq(m, steps):
+        out = []
+        for j in range(steps):
+            z = (ctypes.c_float * m)()
+            lib.degk_oracle_normals_f32(ctypes.c_uint64(seed), ctypes.c_uint64(traj), ctypes.c_uint32(j), m, z)
+            out += list(z)
+        return np.array(out, np.float32)
+    ref = seq(4, 12)                                   # 48 normals = blocks 0..11
+    for m, steps in ((1, 48), (2, 24), (3, 16)):
+        assert np.array_equal(seq(m, steps), ref), m
+    # block 0 from the raw words: u = ((x >> 8) + 1) 2^-24, r = sqrt(-2 ln u1), (r cos 2 pi u2, r sin 2 pi u2)
+    w = (ctypes.c_uint32 * 4)()
+    lib.degk_oracle_philox(0, 0, traj & 0xFFFFFFFF, traj >> 32, seed & 0xFFFFFFFF, seed >> 32, w)
+    u = [np.float32(((x >> 8) + 1) * 2.0 ** -24) for x in w]
+    exp = []
+    for a, b in ((u[0], u[1]), (u[2], u[3])):
+        r = np.sqrt(np.float32(-2) * np.log(a))
+        th = np.float32(6.283185307179586) * b
+        exp += [r * np.cos(th), r * np.sin(th)]
+    assert np.allclose(ref[:4], np.array(exp, np.float32), rtol=2e-6, atol=1e-7)
