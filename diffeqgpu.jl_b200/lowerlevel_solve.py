@@ -276,12 +276,14 @@ class SolvePlan:
         saved = self.stream
         # (thread-local capture mode: other threads of the process -- an NCCL watchdog, a data loader -- may go on
         #  calling the CUDA runtime while this one captures)
-        with torch.cuda.device(self.device), torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
-            self.stream = torch.cuda.current_stream(self.device)
-            for _ in range(int(launches)):
-                self._reset()
-                self._launch()
-        self.stream = saved
+        try:
+            with torch.cuda.device(self.device), torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                self.stream = torch.cuda.current_stream(self.device)
+                for _ in range(int(launches)):
+                    self._reset()
+                    self._launch()
+        finally:
+            self.stream = saved                          # later direct launches go back to the plan's own stream
         self._graph = g
         return self
 
