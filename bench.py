@@ -76,15 +76,20 @@ class ClockSampler:
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU path.  Julia is not installed on the box,
-    so this is the oracle port (oracle/degk_oracle.cpp, OpenMP over trajectories, all host
-    threads) on a bounded sample of the same workload."""
+    """--impl reference: the reference algorithm's CPU path.  Where `julia` and the reference's packages exist the
+    reference itself is timed (run_reference_julia); they are not installed on the build image or the GPU box, so there
+    this is the oracle port (oracle/degk_oracle.cpp, OpenMP over trajectories, all host threads) on a bounded sample
+    of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle
     cores = os.cpu_count() or 1
     n = args.ref_traj
+    julia = run_reference_julia(args, n, cores)
+    if julia is not None:
+        print(json.dumps(julia))
+        return
+    from oracle import oracle
     rng = np.random.default_rng(0)
     times, steps = [], 0
     for i in range(args.warmup + args.steps):
@@ -107,6 +112,32 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def run_reference_julia(args, n, cores):
+    """The reference itself, where it can run: `julia` on PATH with DiffEqGPU / OrdinaryDiffEq installed (neither is in
+    this image or on the GPU box).  baseline/run_reference.jl times EnsembleGPUKernel(CPU()) + GPUTsit5 and
+    EnsembleThreads() + Tsit5 on the C2 workload; the kernel-path arm becomes the line (kind "reference").  Any failure
+    -- no julia, missing packages, time-out -- returns None and the oracle port is timed instead."""
+    import shutil
+    exe = shutil.which("julia")
+    if not exe or os.environ.get("DEGK_BENCH_NO_JULIA"):
+        return None
+    try:
+        out = subprocess.run([exe, "-t", "auto", str(ROOT / "baseline" / "run_reference.jl"), str(n)], capture_output=True,
+                             text=True, timeout=900, cwd=str(ROOT))
+        arms = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+        arm = next(a for a in arms if "EnsembleGPUKernel" in a["arm"])
+    except Exception:
+        return None
+    value = float(arm["value"])
+    sample = f"{n} trajectories of the C2 workload through {arm['arm']} (baseline/run_reference.jl)"
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": "trajectory-steps/s", "n_gpus": args.gpus,
+            "steps": 1, "warmup": 1, "ms_per_step": 1e3 * float(arm["seconds"]), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.traj), "sample": sample, "other_arms": [a for a in arms if a is not arm]},
+            "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": int(arm.get("cores", cores)), "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def measure_fma_peak(torch, dev):
