@@ -255,7 +255,9 @@ def lower_function(f, n_state, n_param, jac=False):
         ja = [(f"J[{i}][{j}]", sympy.diff(du[i], u[j])) for i in range(n_state) for j in range(n_state)]
         out["jac"] = _emit([(l, e) for l, e in ja if e != 0])
         tg = [(f"dT[{i}]", sympy.diff(du[i], t)) for i in range(n_state)]
-        out["tgrad"] = _emit([(l, e) for l, e in tg if e != 0])
+        # an autonomous right-hand side has no time gradient: leaving the body out (instead of an empty one) tells the
+        # library so, and the fast build drops the dT terms of the Rosenbrock stages (TGRAD_ZERO, degk_jit.cpp)
+        out["tgrad"] = _emit([(l, e) for l, e in tg if e != 0]) or None
     return out
 
 

@@ -97,7 +97,7 @@ def test_lowering_keeps_two_term_expression_trees():
     import diffeqgpu_b200 as dg
     func = dg.ODEFunction.from_python(lorenz_py, 3, 3, jac=True)
     assert "du[0] = p[0]*(-u[0] + u[1]);" in func.rhs and "du[1] = u[0]*(p[1] - u[2]) - u[1];" in func.rhs
-    assert func.jac.count("J[") == 8 and "J[0][2]" not in func.jac and func.tgrad == ""
+    assert func.jac.count("J[") == 8 and "J[0][2]" not in func.jac and func.tgrad is None          # autonomous: no time-gradient body at all (TGRAD_ZERO)
     plain = dg.ODEFunction.from_python(lorenz_py, 3, 3)
     assert plain.jac is None and plain.tgrad is None and plain.n_state == 3 and plain.n_param == 3
     # float-literal exponents that are integers or halves stay products / square roots (no exp-log detour, which
@@ -308,7 +308,7 @@ def test_lowering_fuzz_against_the_host_functions(tmp_path):
     for k, f in enumerate(funcs):
         code.append(f"""extern "C" void f{k}(double* du, double* Jo, double* dT, const double* u, const double* p, double t) {{
     typedef double T; T J[{n}][{n}] = {{}}; for (int i = 0; i < {n}; ++i) dT[i] = 0;
-    {{ {f.rhs} }} {{ {f.jac} }} {{ {f.tgrad} }}
+    {{ {f.rhs} }} {{ {f.jac} }} {{ {f.tgrad or ""} }}
     for (int i = 0; i < {n}; ++i) for (int j = 0; j < {n}; ++j) Jo[i * {n} + j] = J[i][j]; }}""")
     src = tmp_path / "fuzz.cpp"
     src.write_text("\n".join(code))
