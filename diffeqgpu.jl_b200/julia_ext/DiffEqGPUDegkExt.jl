@@ -126,6 +126,9 @@ function lower_symbolic(rhs, u, p, t; jac::Bool = true, Symbolics = Main.Symboli
     jbody = c_body(J_c, "Jflat")
     jsrc = "    T Jflat[$(n * n)];\n" * jbody * "\n    for (int i = 0; i < $n; ++i) for (int j = 0; j < $n; ++j) J[i][j] = Jflat[i * $n + j];\n"
     dT = Symbolics.derivative.(rhs, (t,))
+    # an autonomous right-hand side: no time-gradient body at all -- a Jacobian body without one tells the library that
+    # dT == 0, and the fast build drops the dT terms of the Rosenbrock stages (TGRAD_ZERO, degk_jit.cpp)
+    all(iszero, dT) && return DegkFunction(rhs = fn.rhs, jac = jsrc)
     T_c = Symbolics.build_function(dT, u, p, t; target = Symbolics.CTarget())
     return DegkFunction(rhs = fn.rhs, jac = jsrc, tgrad = c_body(T_c, "dT"))
 end
